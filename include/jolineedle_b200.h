@@ -1,0 +1,208 @@
+/*
+ * jolineedle_b200 -- C ABI of the B200-native gaze-environment hot path.
+ *
+ * The reference (jolibrain/jolineedle) is pure Python: it has no plugin / operator / FFI
+ * boundary of its own.  Each entry point below therefore cites the reference *Python*
+ * function whose work it replaces (paths relative to the reference root).  All pointers are
+ * plain device pointers unless marked HOST; the library borrows them for the duration of the
+ * call and owns nothing but the opaque handles it hands out.  Every launch goes to the
+ * `stream` argument (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *
+ * Return value: 0 (JN_OK) on success, a jn_status code otherwise; jn_last_error() gives a
+ * thread-local, human-readable description of the last failure.
+ *
+ * Conventions shared by all entry points
+ *   - positions are int64 [n, 2] in (row, col) = (y, x) PATCH coordinates (torch.long, as in
+ *     the reference: general_env.py:118-123);
+ *   - action codes are the reference's (src/env/common.py:4-15): 0 LEFT, 1 RIGHT, 2 UP,
+ *     3 DOWN, 4 LEFT_UP, 5 RIGHT_UP, 6 LEFT_DOWN, 7 RIGHT_DOWN, 8 STOP;
+ *   - boxes are int64 [.., 4] in x1, y1, x2, y2 PIXEL coordinates (src/utils.py:95-106);
+ *   - patch bitmaps are uint32 words, bit (y * cols + x) & 31 of word (y * cols + x) >> 5,
+ *     `jn_bitmap_words(rows, cols)` words per episode;
+ *   - bool tensors are one byte per element holding 0 or 1 (torch.bool storage).
+ */
+#ifndef JOLINEEDLE_B200_H
+#define JOLINEEDLE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JN_ABI_VERSION 1
+
+typedef enum jn_status {
+  JN_OK = 0,
+  JN_ERR_INVALID = 1,     /* bad argument (maps to AssertionError / ValueError on the Python side) */
+  JN_ERR_CUDA = 2,        /* a CUDA runtime / driver call failed */
+  JN_ERR_UNSUPPORTED = 3, /* valid request that this build does not cover */
+  JN_ERR_NO_DEVICE = 4    /* no sm_100 device visible */
+} jn_status;
+
+typedef enum jn_dtype { JN_U8 = 0, JN_F32 = 1 } jn_dtype;
+
+/* jn_gather flags */
+#define JN_GATHER_NORMALIZE 1u /* uint8 source -> float32 output, value / 255 (ToTensor, dataset.py:240) */
+#define JN_GATHER_FOCUS 2u     /* output in YOLOX Focus space-to-depth layout [4*C, P/2, P/2] */
+
+/* jn_gather engine selection (JN_ENGINE_AUTO picks the fastest one the shapes allow) */
+typedef enum jn_engine {
+  JN_ENGINE_AUTO = 0,
+  JN_ENGINE_TENSOR = 1, /* TMA tensor-map tiles  (cp.async.bulk.tensor, SASS UTMALDG)  */
+  JN_ENGINE_BULK = 2,   /* TMA row copies        (cp.async.bulk,        SASS UBLKCP)   */
+  JN_ENGINE_LDG = 3     /* plain global loads: any alignment, any stride (slow, always valid) */
+} jn_engine;
+
+/* overlap rules of jn_patch_bitmaps */
+typedef enum jn_overlap_rule {
+  JN_RULE_ANY_PIXEL = 0, /* NeedleGeneralEnv.convert_bboxes_to_masks, general_env.py:360-379 */
+  JN_RULE_AREA5 = 1      /* NeedleSimpleEnv.bbox_positions (>5% of P^2 or centre), simple_env.py:270-321 */
+} jn_overlap_rule;
+
+int jn_abi_version(void);
+const char* jn_last_error(void);
+/* SM count and compute capability of the current device. */
+int jn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+static inline int jn_bitmap_words(int rows, int cols) { return (rows * cols + 31) / 32; }
+/* Host-only self test of arithmetic shared with the kernels (runs without a GPU):
+ * unit_out HOST float[256] <- the uint8 -> value/255 normalisation of every byte value;
+ * direction_out HOST int[9] <- action code for gradient signs, index (sign(dy)+1)*3 + sign(dx)+1
+ * (the decision table of move_towards, simple_env.py:84-125). */
+int jn_selftest_host(float* unit_out, int* direction_out);
+
+/* ------------------------------------------------------------------------------------------
+ * Image sets: where glimpses are gathered from.
+ *
+ * An image set describes `n_slabs` device allocations, slab k holding `counts[k]` images of
+ * shape [C, heights[k], widths[k]] back to back (a [B, C, H, W] batch is one slab; a python
+ * list of [C, H, W] tensors is B slabs of one image).  Images are numbered in slab order.
+ * Creating a set encodes the TMA tensor maps for it.  Replaces the `self.images` /
+ * `self.image` members of the reference envs (general_env.py:84-115 with n_glimps_levels=1,
+ * simple_env.py:184) -- no pixel is copied.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct jn_images jn_images;
+
+int jn_images_create(jn_images** out, int n_slabs, const void* const* slab_ptrs /*HOST*/,
+                     const int32_t* counts /*HOST*/, const int32_t* heights /*HOST*/,
+                     const int32_t* widths /*HOST*/, int channels, int dtype /*jn_dtype*/,
+                     int patch_size, void* stream);
+void jn_images_destroy(jn_images* set);
+/* 1 if the TMA engines can serve this set (16-byte aligned bases / rows / patches), else 0. */
+int jn_images_tma_ok(const jn_images* set, int engine /*jn_engine*/);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  glimpse gather.
+ *
+ * For item i in [0, n_items): image = src_index ? src_index[i] : i (negative -> the output
+ * tile is zero-filled), (y, x) = positions[i]; copies the [C, P, P] tile at patch (y, x) of
+ * that image to out + i * out_item_stride_bytes.  Output dtype = source dtype, or float32
+ * with JN_GATHER_NORMALIZE; layout [C, P, P], or [4C, P/2, P/2] with JN_GATHER_FOCUS
+ * (out[(dy + 2*dx) * C + c][i][j] = tile[c][2i + dy][2j + dx], the YOLOX Focus stem order
+ * TL, BL, TR, BR).
+ *
+ * Replaces: NeedleGeneralEnv.patches (general_env.py:285-306), get_patch (simple_env.py:55-81)
+ * plus the per-step copy into the sample (simple_env.py:472), the patch loop of
+ * get_detection_batch (general_env.py:531-542) and of init_sample (simple_env.py:417-419).
+ *
+ * `status` (device int32[1], may be NULL) is OR-ed with 1 if some position was outside the
+ * patch grid (that tile is skipped).
+ * ------------------------------------------------------------------------------------------ */
+int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src_index,
+              int n_items, void* out, int64_t out_item_stride_bytes, uint32_t flags,
+              int engine /*jn_engine*/, int32_t* status, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K0  patch x bbox overlap tables.
+ * ------------------------------------------------------------------------------------------ */
+/* bboxes int64 [n, max_boxes, 4]; n_boxes int32 [n] or NULL (= all max_boxes rows are real);
+ * rows/cols int32 [n] per-episode grid or NULL (= the scalars grid_rows/grid_cols);
+ * out uint32 [n, words_per_item].  Replaces convert_bboxes_to_masks (general_env.py:360-379)
+ * and bbox_positions (simple_env.py:270-321). */
+int jn_patch_bitmaps(const int64_t* bboxes, const int32_t* n_boxes, int n, int max_boxes,
+                     int patch_size, int grid_rows, int grid_cols, const int32_t* rows,
+                     const int32_t* cols, int rule /*jn_overlap_rule*/, uint32_t* out,
+                     int words_per_item, void* stream);
+/* uint32 bitmaps -> one byte per patch, [n, rows, cols] (the reference's bool tensors). */
+int jn_bitmap_unpack(const uint32_t* words, int n, int rows, int cols, uint8_t* out, void* stream);
+/* Per-patch split of each box: local int64 [n, rows, cols, max_boxes, 4] (inclusive local
+ * x1,y1,x2,y2, clamped to P-1) and present uint8 [n, rows, cols, max_boxes].  Replaces
+ * parse_bboxes (general_env.py:381-504).  `status` gets bit 2 set when a box corner falls
+ * outside the grid (the reference raises IndexError there). */
+int jn_split_boxes(const int64_t* bboxes, int n, int max_boxes, int patch_size, int rows, int cols,
+                   int64_t* local, uint8_t* present, int32_t* status, void* stream);
+/* Per item the intersection of every raw box with patch (y, x) as float32
+ * [n_items, max_boxes, 6] rows (0, x1, y1, x2, y2, 1) in local pixels, zero rows when empty.
+ * episode = src_index ? src_index[i] : i (negative -> zero rows).  Replaces
+ * NeedleSimpleEnv.local_bboxes (simple_env.py:231-268). */
+int jn_local_boxes(const int64_t* bboxes, const int32_t* n_boxes, int max_boxes, int patch_size,
+                   const int64_t* positions, const int32_t* src_index, int n_items, float* out,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  batched env reset / step (one warp per episode).
+ * ------------------------------------------------------------------------------------------ */
+/* Clears visited / steps / has_stopped and marks the start patch.  Replaces
+ * init_env_variables + the tail of reset (general_env.py:117-142,164). */
+int jn_env_reset(const int64_t* positions, uint32_t* visited, int64_t* steps, uint8_t* has_stopped,
+                 int n, int rows, int cols, int32_t* status, void* stream);
+/* One env step, in the reference's order (general_env.py:172-207): move + clamp, sticky STOP
+ * flag, reward from the visited map BEFORE marking, mark, steps += 1, truncated, terminated.
+ *   reward = fl32(fl32(fresh + fl32(-1/T)) + stop_eval)      (general_env.py:321-358)
+ * `cost` is the host-rounded float32 of -1/max_ep_len.  pos_in and pos_out may alias.
+ * `status` gets bit 1 set when an action code is outside [0, 8]. */
+int jn_env_step(const int64_t* pos_in, const int64_t* actions, int64_t* pos_out, uint32_t* visited,
+                const uint32_t* bbox, int64_t* steps, uint8_t* has_stopped, float* rewards,
+                uint8_t* terminated, uint8_t* truncated, int n, int rows, int cols,
+                int max_ep_len, float cost, int stop_enabled, int32_t* status, void* stream);
+/* prop_patches_found (general_env.py:308-315) as float32 [n]; `terminated` (general_env.py:
+ * 235-246, uint8 [n]) is written too when non-NULL. */
+int jn_env_props(const uint32_t* visited, const uint32_t* bbox, const uint8_t* has_stopped, int n,
+                 int rows, int cols, int stop_enabled, float* prop_patches, uint8_t* terminated,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  segmented scans.
+ * ------------------------------------------------------------------------------------------ */
+/* Returns tail of a rollout (reinforce.py:186-202).  Inputs are step-major as the env
+ * produces them: rewards float32 [T, n], terminated uint8 [T, n].  Outputs are episode-major
+ * like the reference's stacked tensors: rewards_out [n, T], masks uint8 [n, T+1] (column 0
+ * = 1, column t+1 = !terminated[t]), logit_masks uint8 [n, T], returns float32 [n, T] with
+ * returns[:, t] = sum_{s >= t} rewards[:, s] * logit_masks[:, s], accumulated in float64
+ * from the last step and rounded once per element (torch CPU cumsum semantics). */
+int jn_returns(const float* rewards_tn, const uint8_t* terminated_tn, int T, int n,
+               float* rewards_out, uint8_t* masks, uint8_t* logit_masks, float* returns,
+               void* stream);
+/* Same scan on episode-major inputs: rewards [n, T] (row stride in elements), logit_masks
+ * uint8 [n, T]. */
+int jn_returns_rows(const float* rewards, int64_t rewards_row_stride, const uint8_t* logit_masks,
+                    int64_t masks_row_stride, int T, int n, float* returns, void* stream);
+
+/* Supervised trajectories from supplied keypoints (simple_env.py:481-664).
+ *
+ * Episode e walks from start[e] through its segments seg_begin[e] .. seg_begin[e+1]-1.
+ * Segment k is a straight-line walk (8-neighbour, diagonal first) to (seg_to_y, seg_to_x);
+ * the recorded best action points at (seg_tgt_y, seg_tgt_x); seg_flags bit 0 marks the first
+ * segment of a keypoint group (the "previous best action" overwrite, simple_env.py:548-552).
+ * Whenever a best action would be STOP the next pre-drawn replacement move is consumed from
+ * draws[draw_begin[e] ..] in the reference's draw order (simple_env.py:715-718).
+ * Episodes longer than T keep their LAST T records (simple_env.py:573-584); shorter ones are
+ * zero-padded with masks = 0.
+ *
+ * Outputs, all [n, T, ...]: positions int64 [.,2], current_actions / next_actions / labels
+ * int64, masks float32, gather_src int32 (= e for recorded slots, -1 for padding; feed it
+ * to jn_gather / jn_local_boxes together with `positions`), ep_len int32 [n] (untruncated).
+ * labels = membership of the position in `area_bitmaps` (JN_RULE_AREA5 words, per-episode
+ * grid cols from `cols`). */
+int jn_traj_expand(const int32_t* start_yx /*[n,2]*/, const int32_t* seg_begin /*[n+1]*/,
+                   const int32_t* seg_to_yx /*[S,2]*/, const int32_t* seg_tgt_yx /*[S,2]*/,
+                   const uint8_t* seg_flags /*[S]*/, const int32_t* draw_begin /*[n+1]*/,
+                   const uint8_t* draws, const uint32_t* area_bitmaps, int words_per_item,
+                   const int32_t* cols /*[n]*/, int n, int T, int64_t* positions,
+                   int64_t* current_actions, int64_t* next_actions, int64_t* labels, float* masks,
+                   int32_t* gather_src, int32_t* ep_len, int32_t* status, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JOLINEEDLE_B200_H */

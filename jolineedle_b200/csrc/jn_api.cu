@@ -1,0 +1,520 @@
+// C ABI of jolineedle_b200 (see include/jolineedle_b200.h): argument validation, TMA tensor-map
+// encoding, launch configuration.  No torch types cross this boundary.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/jolineedle_b200.h"
+#include "jn_env.cuh"
+#include "jn_gather.cuh"
+#include "jn_scan.cuh"
+
+namespace {
+
+thread_local char g_error[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define JN_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t err__ = (expr);                                                                    \
+    if (err__ != cudaSuccess)                                                                      \
+      return fail(JN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+  } while (0)
+
+#define JN_REQUIRE(cond, ...)                              \
+  do {                                                     \
+    if (!(cond)) return fail(JN_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+struct DeviceInfo {
+  int device = -1, sm_count = 0, cc_major = 0, cc_minor = 0, max_smem_optin = 0;
+};
+
+int current_device_info(DeviceInfo& info) {
+  static std::mutex mu;
+  static std::vector<DeviceInfo> cache;
+  int dev = 0;
+  JN_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  for (const auto& d : cache)
+    if (d.device == dev) { info = d; return JN_OK; }
+  DeviceInfo d;
+  d.device = dev;
+  JN_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
+  JN_CUDA(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  JN_CUDA(cudaDeviceGetAttribute(&d.cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+  JN_CUDA(cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  cache.push_back(d);
+  info = d;
+  return JN_OK;
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+inline int grid_for(long long work_items, int per_block, int cap) {
+  long long g = (work_items + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+struct jn_images {
+  int n_slabs = 0, n_images = 0, channels = 0, dtype = 0, elem = 0, patch = 0;
+  // single slab
+  const uint8_t* base = nullptr;
+  int height = 0, width = 0;
+  long long image_stride = 0;
+  // several slabs
+  jnk::ImageRec* d_recs = nullptr;
+  CUtensorMap* d_maps = nullptr;
+  // engines
+  bool bulk_ok = false, tensor_ok = false;
+  int box_w = 0, kbox = 0;
+  CUtensorMap map0;
+  int device = 0;
+};
+
+namespace {
+
+// Largest divisor of `patch` that is <= 256 elements and a multiple of 16 bytes.
+int pick_box_width(int patch, int elem) {
+  for (int w = patch < 256 ? patch : 256; w >= 1; --w)
+    if (patch % w == 0 && (w * elem) % 16 == 0) return w;
+  return 0;
+}
+
+// Rows per chunk: largest divisor of patch (even when `need_even`) with rows*patch*elem <= target.
+int pick_rows(int patch, int elem, int target_bytes, bool need_even) {
+  int best = 0;
+  for (int r = 1; r <= patch && r <= 256; ++r) {
+    if (patch % r) continue;
+    if (need_even && (r & 1)) continue;
+    if ((long long)r * patch * elem <= target_bytes) best = r;
+  }
+  return best;
+}
+
+int encode_slab_map(CUtensorMap* map, const void* ptr, int elem, int n_planes, int height, int width, int box_w,
+                    int kbox, int rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(JN_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  // 4-D view (innermost first): [box_w] x [width / box_w] x [height] x [planes]
+  cuuint64_t dims[4] = {(cuuint64_t)box_w, (cuuint64_t)(width / box_w), (cuuint64_t)height, (cuuint64_t)n_planes};
+  cuuint64_t strides[3] = {(cuuint64_t)box_w * elem, (cuuint64_t)width * elem, (cuuint64_t)width * elem * height};
+  cuuint32_t box[4] = {(cuuint32_t)box_w, (cuuint32_t)kbox, (cuuint32_t)rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUtensorMapDataType dt = elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  CUresult r = fn(map, dt, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(JN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (dims %llu x %llu x %llu x %llu, box %u x %u x %u)",
+                (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                (unsigned long long)dims[3], box[0], box[1], box[2]);
+  return JN_OK;
+}
+
+}  // namespace
+
+namespace {
+
+constexpr int kCopyStages = 6, kCopyAhead = 3;
+constexpr int kXformStages = 4, kXformWarps = 8;
+
+template <typename Kernel>
+int launch_persistent(Kernel kernel, const jnk::GatherArgs& a, const CUtensorMap& map, int threads, size_t smem,
+                      const DeviceInfo& dev, cudaStream_t stream) {
+  JN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  JN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+  if (per_sm < 1) return fail(JN_ERR_CUDA, "gather kernel does not fit on an SM (%zu bytes of shared memory)", smem);
+  long long grid = (long long)dev.sm_count * per_sm;
+  if (grid > a.total_chunks) grid = a.total_chunks;
+  kernel<<<(int)grid, threads, smem, stream>>>(a, map);
+  JN_CUDA(cudaGetLastError());
+  return JN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int jn_abi_version(void) { return JN_ABI_VERSION; }
+const char* jn_last_error(void) { return g_error; }
+
+int jn_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  DeviceInfo d;
+  if (int rc = current_device_info(d)) return rc;
+  if (sm_count) *sm_count = d.sm_count;
+  if (cc_major) *cc_major = d.cc_major;
+  if (cc_minor) *cc_minor = d.cc_minor;
+  return JN_OK;
+}
+
+// Host-only self test of the two pieces of arithmetic shared with the device code: the
+// direction table and the uint8 -> [0,1] normalisation.  `unit_out` receives the 256 values.
+int jn_selftest_host(float* unit_out /*HOST [256]*/, int* direction_out /*HOST [9], index (sy+1)*3+(sx+1)*/) {
+  if (unit_out)
+    for (int i = 0; i < 256; ++i) unit_out[i] = jnk::u8_to_unit((float)i);
+  if (direction_out)
+    for (int sy = -1; sy <= 1; ++sy)
+      for (int sx = -1; sx <= 1; ++sx) direction_out[(sy + 1) * 3 + (sx + 1)] = jnk::direction_code(sy * 3, sx * 5);
+  return JN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// image sets
+// ------------------------------------------------------------------------------------------
+int jn_images_create(jn_images** out, int n_slabs, const void* const* slab_ptrs, const int32_t* counts,
+                     const int32_t* heights, const int32_t* widths, int channels, int dtype, int patch_size,
+                     void* stream) {
+  JN_REQUIRE(out != nullptr, "jn_images_create: out is NULL");
+  *out = nullptr;
+  JN_REQUIRE(n_slabs >= 1 && slab_ptrs && counts && heights && widths, "jn_images_create: empty image set");
+  JN_REQUIRE(dtype == JN_U8 || dtype == JN_F32, "jn_images_create: dtype must be JN_U8 or JN_F32");
+  JN_REQUIRE(channels >= 1 && patch_size >= 1, "jn_images_create: channels and patch_size must be positive");
+  const int elem = dtype == JN_F32 ? 4 : 1;
+  long long total = 0;
+  bool aligned = (patch_size * elem) % 16 == 0;
+  for (int k = 0; k < n_slabs; ++k) {
+    JN_REQUIRE(slab_ptrs[k] != nullptr && counts[k] >= 1, "jn_images_create: slab %d is empty", k);
+    // same precondition as the reference envs (general_env.py:50-51, simple_env.py:68-69)
+    JN_REQUIRE(heights[k] > 0 && widths[k] > 0 && heights[k] % patch_size == 0 && widths[k] % patch_size == 0,
+               "image size %dx%d is not a multiple of patch_size %d", heights[k], widths[k], patch_size);
+    total += counts[k];
+    aligned = aligned && (reinterpret_cast<uintptr_t>(slab_ptrs[k]) % 16 == 0) && ((long long)widths[k] * elem) % 16 == 0;
+  }
+  JN_REQUIRE(total < (1ll << 30), "jn_images_create: too many images");
+
+  jn_images* s = new jn_images();
+  s->n_slabs = n_slabs; s->n_images = (int)total; s->channels = channels; s->dtype = dtype; s->elem = elem;
+  s->patch = patch_size;
+  cudaGetDevice(&s->device);
+  s->bulk_ok = aligned;
+  s->box_w = aligned ? pick_box_width(patch_size, elem) : 0;
+  s->kbox = s->box_w ? patch_size / s->box_w : 0;
+  s->tensor_ok = aligned && s->box_w > 0 && encode_tiled_fn() != nullptr;
+  memset(&s->map0, 0, sizeof(s->map0));
+
+  auto bail = [&](int rc) { jn_images_destroy(s); return rc; };
+  if (n_slabs == 1) {
+    s->base = static_cast<const uint8_t*>(slab_ptrs[0]);
+    s->height = heights[0]; s->width = widths[0];
+    s->image_stride = (long long)channels * heights[0] * widths[0] * elem;
+  } else {
+    std::vector<jnk::ImageRec> recs;
+    recs.reserve((size_t)total);
+    for (int k = 0; k < n_slabs; ++k)
+      for (int i = 0; i < counts[k]; ++i) {
+        jnk::ImageRec r;
+        r.base = static_cast<const uint8_t*>(slab_ptrs[k]) + (long long)i * channels * heights[k] * widths[k] * elem;
+        r.height = heights[k]; r.width = widths[k]; r.map_index = k; r.plane0 = i * channels;
+        recs.push_back(r);
+      }
+    if (cudaMalloc(&s->d_recs, recs.size() * sizeof(jnk::ImageRec)) != cudaSuccess)
+      return bail(fail(JN_ERR_CUDA, "cudaMalloc(image records) failed: %s", cudaGetErrorString(cudaGetLastError())));
+    if (cudaMemcpyAsync(s->d_recs, recs.data(), recs.size() * sizeof(jnk::ImageRec), cudaMemcpyHostToDevice,
+                        (cudaStream_t)stream) != cudaSuccess ||
+        cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess)
+      return bail(fail(JN_ERR_CUDA, "upload of image records failed: %s", cudaGetErrorString(cudaGetLastError())));
+  }
+  *out = s;
+  return JN_OK;
+}
+
+void jn_images_destroy(jn_images* s) {
+  if (!s) return;
+  if (s->d_recs) cudaFree(s->d_recs);
+  if (s->d_maps) cudaFree(s->d_maps);
+  delete s;
+}
+
+int jn_images_tma_ok(const jn_images* s, int engine) {
+  if (!s) return 0;
+  if (engine == JN_ENGINE_TENSOR) return s->tensor_ok && s->n_slabs == 1 ? 1 : 0;
+  if (engine == JN_ENGINE_BULK) return s->bulk_ok ? 1 : 0;
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 gather
+// ------------------------------------------------------------------------------------------
+int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src_index, int n_items, void* out,
+              int64_t out_item_stride_bytes, uint32_t flags, int engine, int32_t* status, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  JN_REQUIRE(set != nullptr, "jn_gather: image set is NULL");
+  JN_REQUIRE(n_items >= 0, "jn_gather: negative item count");
+  if (n_items == 0) return JN_OK;
+  JN_REQUIRE(positions != nullptr && out != nullptr, "jn_gather: NULL positions / out");
+  const bool normalize = (flags & JN_GATHER_NORMALIZE) != 0, focus = (flags & JN_GATHER_FOCUS) != 0;
+  JN_REQUIRE(!(normalize && set->dtype != JN_U8), "JN_GATHER_NORMALIZE needs a uint8 image set");
+  JN_REQUIRE(!(focus && (set->patch % 2)), "JN_GATHER_FOCUS needs an even patch size");
+  JN_REQUIRE(src_index != nullptr || n_items <= set->n_images,
+             "jn_gather: %d items but only %d images and no src_index", n_items, set->n_images);
+  const int P = set->patch, C = set->channels;
+  const int out_elem = (normalize || set->dtype == JN_F32) ? 4 : 1;
+  const long long tile_out_bytes = (long long)C * P * P * out_elem;
+  JN_REQUIRE(out_item_stride_bytes >= tile_out_bytes, "jn_gather: out_item_stride_bytes %lld < tile size %lld",
+             (long long)out_item_stride_bytes, tile_out_bytes);
+  DeviceInfo dev;
+  if (int rc = current_device_info(dev)) return rc;
+
+  jnk::GatherArgs a;
+  memset(&a, 0, sizeof(a));
+  a.base = set->base; a.images = set->d_recs; a.maps = nullptr;
+  a.positions = positions; a.src_index = src_index;
+  a.out = static_cast<uint8_t*>(out); a.out_item_stride = out_item_stride_bytes; a.image_stride = set->image_stride;
+  a.status = status; a.n_items = n_items; a.n_images = set->n_images;
+  a.channels = C; a.height = set->height; a.width = set->width; a.patch = P; a.elem = set->elem;
+  a.box_w = set->box_w; a.kbox = set->kbox;
+
+  const bool plain_copy = !normalize && !focus;
+  const bool out_aligned = reinterpret_cast<uintptr_t>(out) % 16 == 0 && out_item_stride_bytes % 16 == 0;
+  // u8 -> u8 Focus has no TMA kernel (nobody asks for it); it runs on the LDG engine.
+  const bool tma_mode = plain_copy || normalize || (focus && set->dtype == JN_F32);
+  if (engine == JN_ENGINE_AUTO) {
+    if (!tma_mode || !out_aligned || !set->bulk_ok) engine = JN_ENGINE_LDG;
+    else engine = (set->tensor_ok && set->n_slabs == 1) ? JN_ENGINE_TENSOR : JN_ENGINE_BULK;
+  }
+  if (engine == JN_ENGINE_TENSOR)
+    JN_REQUIRE(tma_mode && out_aligned && set->tensor_ok && set->n_slabs == 1,
+               "tensor-map engine unavailable for this image set / flags (needs one slab, 16-byte aligned rows)");
+  if (engine == JN_ENGINE_BULK)
+    JN_REQUIRE(tma_mode && out_aligned && set->bulk_ok, "bulk engine needs 16-byte aligned bases, rows and patches");
+
+  if (engine == JN_ENGINE_LDG) {
+    a.rows = 1; a.chunks_per_plane = P; a.total_chunks = 0;
+    const long long total = (long long)n_items * C * P * P;
+    const int grid = grid_for(total, 256 * 8, dev.sm_count * 16);
+    jnk::gather_ldg_kernel<<<grid, 256, 0, stream>>>(a, out_elem == 4, normalize, focus);
+    JN_CUDA(cudaGetLastError());
+    return JN_OK;
+  }
+
+  // TMA engines: chunk geometry
+  const int target = plain_copy ? 32768 : (set->elem == 4 ? 24576 : 16384);
+  const int rows = pick_rows(P, set->elem, target, focus);
+  JN_REQUIRE(rows > 0, "patch row of %d bytes does not fit a shared-memory stage", P * set->elem);
+  a.rows = rows; a.chunks_per_plane = P / rows;
+  const long long total_chunks = (long long)n_items * C * a.chunks_per_plane;
+  JN_REQUIRE(total_chunks < (1ll << 31) - (1ll << 22), "jn_gather: too many chunks (%lld)", total_chunks);
+  a.total_chunks = (int)total_chunks;
+  const size_t chunk_bytes = (size_t)rows * P * set->elem;
+
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (engine == JN_ENGINE_TENSOR) {
+    if (int rc = encode_slab_map(&map, set->base, set->elem, set->n_images * C, set->height, set->width, set->box_w,
+                                 set->kbox, rows))
+      return rc;
+  }
+
+  if (plain_copy) {
+    const size_t smem = kCopyStages * chunk_bytes + jnk::kZeroBytes + kCopyStages * sizeof(uint64_t);
+    if (engine == JN_ENGINE_TENSOR)
+      return launch_persistent(jnk::gather_copy_kernel<kCopyStages, kCopyAhead, true>, a, map, 32, smem, dev, stream);
+    return launch_persistent(jnk::gather_copy_kernel<kCopyStages, kCopyAhead, false>, a, map, 32, smem, dev, stream);
+  }
+  const size_t smem = kXformStages * chunk_bytes + 2 * kXformStages * sizeof(uint64_t);
+  const int threads = (kXformWarps + 1) * 32;
+  const bool tensor = engine == JN_ENGINE_TENSOR;
+#define JN_XFORM(mode)                                                                                           \
+  (tensor ? launch_persistent(jnk::gather_xform_kernel<mode, kXformStages, kXformWarps, true>, a, map, threads, smem, \
+                              dev, stream)                                                                       \
+          : launch_persistent(jnk::gather_xform_kernel<mode, kXformStages, kXformWarps, false>, a, map, threads,  \
+                              smem, dev, stream))
+  if (normalize && !focus) return JN_XFORM(jnk::kNormPlain);
+  if (normalize && focus) return JN_XFORM(jnk::kNormFocus);
+  return JN_XFORM(jnk::kF32Focus);
+#undef JN_XFORM
+}
+
+// ------------------------------------------------------------------------------------------
+// K0 tables
+// ------------------------------------------------------------------------------------------
+int jn_patch_bitmaps(const int64_t* bboxes, const int32_t* n_boxes, int n, int max_boxes, int patch_size,
+                     int grid_rows, int grid_cols, const int32_t* rows, const int32_t* cols, int rule, uint32_t* out,
+                     int words_per_item, void* stream) {
+  JN_REQUIRE(n >= 0 && max_boxes >= 0 && patch_size >= 1, "jn_patch_bitmaps: bad sizes");
+  if (n == 0) return JN_OK;
+  JN_REQUIRE(out != nullptr && (bboxes != nullptr || max_boxes == 0), "jn_patch_bitmaps: NULL pointer");
+  JN_REQUIRE(rule == JN_RULE_ANY_PIXEL || rule == JN_RULE_AREA5, "jn_patch_bitmaps: unknown rule %d", rule);
+  JN_REQUIRE((rows && cols) || (grid_rows >= 1 && grid_cols >= 1), "jn_patch_bitmaps: grid size missing");
+  JN_REQUIRE((rows && cols) ? words_per_item >= 1 : words_per_item >= jn_bitmap_words(grid_rows, grid_cols),
+             "jn_patch_bitmaps: words_per_item too small");
+  DeviceInfo dev;
+  if (int rc = current_device_info(dev)) return rc;
+  const int wpb = 4;
+  jnk::patch_bitmaps_kernel<<<grid_for(n, wpb, dev.sm_count * 8), wpb * 32, 0, (cudaStream_t)stream>>>(
+      bboxes, n_boxes, n, max_boxes, patch_size, grid_rows, grid_cols, rows, cols, rule, out, words_per_item);
+  JN_CUDA(cudaGetLastError());
+  return JN_OK;
+}
+
+int jn_bitmap_unpack(const uint32_t* words, int n, int rows, int cols, uint8_t* out, void* stream) {
+  JN_REQUIRE(n >= 0 && rows >= 1 && cols >= 1, "jn_bitmap_unpack: bad sizes");
+  if (n == 0) return JN_OK;
+  JN_REQUIRE(words && out, "jn_bitmap_unpack: NULL pointer");
+  DeviceInfo dev;
+  if (int rc = current_device_info(dev)) return rc;
+  const long long total = (long long)n * rows * cols;
+  jnk::bitmap_unpack_kernel<<<grid_for(total, 256, dev.sm_count * 8), 256, 0, (cudaStream_t)stream>>>(
+      words, n, rows * cols, jn_bitmap_words(rows, cols), out);
+  JN_CUDA(cudaGetLastError());
+  return JN_OK;
+}
+
+int jn_split_boxes(const int64_t* bboxes, int n, int max_boxes, int patch_size, int rows, int cols, int64_t* local,
+                   uint8_t* present, int32_t* status, void* stream) {
+  JN_REQUIRE(n >= 0 && max_boxes >= 0 && patch_size >= 1 && rows >= 1 && cols >= 1, "jn_split_boxes: bad sizes");
+  const long long total = (long long)n * rows * cols * max_boxes;
+  if (total == 0) return JN_OK;
+  JN_REQUIRE(bboxes && local && present, "jn_split_boxes: NULL pointer");
+  DeviceInfo dev;
+  if (int rc = current_device_info(dev)) return rc;
+  jnk::split_boxes_kernel<<<grid_for(total, 256, dev.sm_count * 8), 256, 0, (cudaStream_t)stream>>>(
+      bboxes, n, max_boxes, patch_size, rows, cols, local, present, status);
+  JN_CUDA(cudaGetLastError());
+  return JN_OK;
+}
+
+int jn_local_boxes(const int64_t* bboxes, const int32_t* n_boxes, int max_boxes, int patch_size,
+                   const int64_t* positions, const int32_t* src_index, int n_items, float* out, void* stream) {
+  JN_REQUIRE(n_items >= 0 && max_boxes >= 0 && patch_size >= 1, "jn_local_boxes: bad sizes");
+  const long long total = (long long)n_items * max_boxes;
+  if (total == 0) return JN_OK;
+  JN_REQUIRE(bboxes && positions && out, "jn_local_boxes: NULL pointer");
+  DeviceInfo dev;
+  if (int rc = current_device_info(dev)) return rc;
+  jnk::local_boxes_kernel<<<grid_for(total, 256, dev.sm_count * 8), 256, 0, (cudaStream_t)stream>>>(
+      bboxes, n_boxes, max_boxes, patch_size, positions, src_index, n_items, out);
+  JN_CUDA(cudaGetLastError());
+  return JN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 env
+// ------------------------------------------------------------------------------------------
+int jn_env_reset(const int64_t* positions, uint32_t* visited, int64_t* steps, uint8_t* has_stopped, int n, int rows,
+                 int cols, int32_t* status, void* stream) {
+  JN_REQUIRE(n >= 0 && rows >= 1 && cols >= 1, "jn_env_reset: bad sizes");
+  if (n == 0) return JN_OK;
+  JN_REQUIRE(positions && visited && steps && has_stopped, "jn_env_reset: NULL pointer");
+  DeviceInfo dev;
+  if (int rc = current_device_info(dev)) return rc;
+  const int wpb = 4;
+  jnk::env_reset_kernel<<<grid_for(n, wpb, dev.sm_count * 16), wpb * 32, 0, (cudaStream_t)stream>>>(
+      positions, visited, steps, has_stopped, n, rows, cols, jn_bitmap_words(rows, cols), status);
+  JN_CUDA(cudaGetLastError());
+  return JN_OK;
+}
+
+int jn_env_step(const int64_t* pos_in, const int64_t* actions, int64_t* pos_out, uint32_t* visited,
+                const uint32_t* bbox, int64_t* steps, uint8_t* has_stopped, float* rewards, uint8_t* terminated,
+                uint8_t* truncated, int n, int rows, int cols, int max_ep_len, float cost, int stop_enabled,
+                int32_t* status, void* stream) {
+  JN_REQUIRE(n >= 0 && rows >= 1 && cols >= 1 && max_ep_len >= 1, "jn_env_step: bad sizes");
+  if (n == 0) return JN_OK;
+  JN_REQUIRE(pos_in && actions && pos_out && visited && bbox && steps && has_stopped && rewards && terminated &&
+                 truncated,
+             "jn_env_step: NULL pointer");
+  DeviceInfo dev;
+  if (int rc = current_device_info(dev)) return rc;
+  const int wpb = 4;
+  jnk::env_step_kernel<<<grid_for(n, wpb, dev.sm_count * 16), wpb * 32, 0, (cudaStream_t)stream>>>(
+      pos_in, actions, pos_out, visited, bbox, steps, has_stopped, rewards, terminated, truncated, n, rows, cols,
+      jn_bitmap_words(rows, cols), max_ep_len, cost, stop_enabled, status);
+  JN_CUDA(cudaGetLastError());
+  return JN_OK;
+}
+
+int jn_env_props(const uint32_t* visited, const uint32_t* bbox, const uint8_t* has_stopped, int n, int rows, int cols,
+                 int stop_enabled, float* prop_patches, uint8_t* terminated, void* stream) {
+  JN_REQUIRE(n >= 0 && rows >= 1 && cols >= 1, "jn_env_props: bad sizes");
+  if (n == 0) return JN_OK;
+  JN_REQUIRE(visited && bbox && (has_stopped || !stop_enabled || !terminated), "jn_env_props: NULL pointer");
+  DeviceInfo dev;
+  if (int rc = current_device_info(dev)) return rc;
+  const int wpb = 4;
+  jnk::env_props_kernel<<<grid_for(n, wpb, dev.sm_count * 16), wpb * 32, 0, (cudaStream_t)stream>>>(
+      visited, bbox, has_stopped, n, jn_bitmap_words(rows, cols), stop_enabled, prop_patches, terminated);
+  JN_CUDA(cudaGetLastError());
+  return JN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 scans
+// ------------------------------------------------------------------------------------------
+int jn_returns(const float* rewards_tn, const uint8_t* terminated_tn, int T, int n, float* rewards_out,
+               uint8_t* masks, uint8_t* logit_masks, float* returns, void* stream) {
+  JN_REQUIRE(T >= 0 && n >= 0, "jn_returns: bad sizes");
+  if (n == 0) return JN_OK;
+  JN_REQUIRE(masks && (T == 0 || (rewards_tn && terminated_tn && rewards_out && logit_masks && returns)),
+             "jn_returns: NULL pointer");
+  jnk::returns_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards_tn, terminated_tn, T, n, rewards_out,
+                                                                         masks, logit_masks, returns);
+  JN_CUDA(cudaGetLastError());
+  return JN_OK;
+}
+
+int jn_returns_rows(const float* rewards, int64_t rewards_row_stride, const uint8_t* logit_masks,
+                    int64_t masks_row_stride, int T, int n, float* returns, void* stream) {
+  JN_REQUIRE(T >= 0 && n >= 0, "jn_returns_rows: bad sizes");
+  if (n == 0 || T == 0) return JN_OK;
+  JN_REQUIRE(rewards && logit_masks && returns, "jn_returns_rows: NULL pointer");
+  jnk::returns_rows_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards, rewards_row_stride, logit_masks,
+                                                                              masks_row_stride, T, n, returns);
+  JN_CUDA(cudaGetLastError());
+  return JN_OK;
+}
+
+int jn_traj_expand(const int32_t* start_yx, const int32_t* seg_begin, const int32_t* seg_to_yx,
+                   const int32_t* seg_tgt_yx, const uint8_t* seg_flags, const int32_t* draw_begin,
+                   const uint8_t* draws, const uint32_t* area_bitmaps, int words_per_item, const int32_t* cols, int n,
+                   int T, int64_t* positions, int64_t* current_actions, int64_t* next_actions, int64_t* labels,
+                   float* masks, int32_t* gather_src, int32_t* ep_len, int32_t* status, void* stream) {
+  JN_REQUIRE(n >= 0 && T >= 1 && words_per_item >= 1, "jn_traj_expand: bad sizes");
+  if (n == 0) return JN_OK;
+  JN_REQUIRE(start_yx && seg_begin && draw_begin && area_bitmaps && cols && positions && current_actions &&
+                 next_actions && labels && masks && gather_src && ep_len,
+             "jn_traj_expand: NULL pointer");
+  DeviceInfo dev;
+  if (int rc = current_device_info(dev)) return rc;
+  jnk::traj_expand_kernel<<<grid_for(n, jnk::kTrajWarps, dev.sm_count * 8), jnk::kTrajWarps * 32, 0,
+                           (cudaStream_t)stream>>>(start_yx, seg_begin, seg_to_yx, seg_tgt_yx, seg_flags, draw_begin,
+                                                   draws, area_bitmaps, words_per_item, cols, n, T, positions,
+                                                   current_actions, next_actions, labels, masks, gather_src, ep_len,
+                                                   status);
+  JN_CUDA(cudaGetLastError());
+  return JN_OK;
+}
+
+}  // extern "C"

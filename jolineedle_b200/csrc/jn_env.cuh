@@ -1,0 +1,255 @@
+// K0 (patch x bbox tables) and K2 (warp-per-episode reset / step / props).
+//
+// Bitmap convention: patch (y, x) of an episode with `cols` columns is bit (y*cols + x) & 31
+// of word (y*cols + x) >> 5.  A warp owns one episode; lane l holds words l, l+32, ... in
+// registers while it works, so a 32x32 grid (1024 patches, BASELINE cfg 4) is exactly one
+// word per lane and every count is a popc + warp reduction.
+#pragma once
+
+#include "jn_device.cuh"
+
+namespace jnk {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+
+__device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(kFullMask, v); }
+
+// ------------------------------------------------------------------------------------------
+// K0: overlap bitmaps
+// ------------------------------------------------------------------------------------------
+// rule 0 (any pixel): general_env.py:360-379 -- box rasterised with inclusive x2/y2 after
+//   clamping to the image, max-pooled by P: patch set iff it meets [x1c, x2c) x [y1c, y2c).
+// rule 1 (area 5%): simple_env.py:270-321 -- patch set iff it lies in the box's patch range
+//   and 20 * overlap_area > P^2 (the float test `area / P**2 > 0.05` in exact integers), or
+//   it holds the box centre; always restricted to the grid.
+__global__ void patch_bitmaps_kernel(const int64_t* __restrict__ bboxes, const int32_t* __restrict__ n_boxes, int n,
+                                     int max_boxes, int P, int grid_rows, int grid_cols,
+                                     const int32_t* __restrict__ rows_arr, const int32_t* __restrict__ cols_arr,
+                                     int rule, uint32_t* __restrict__ out, int words_per_item) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int e = blockIdx.x * warps_per_block + (threadIdx.x >> 5); e < n; e += gridDim.x * warps_per_block) {
+    const int rows = rows_arr ? rows_arr[e] : grid_rows;
+    const int cols = cols_arr ? cols_arr[e] : grid_cols;
+    const int nb = n_boxes ? n_boxes[e] : max_boxes;
+    const long long H = (long long)rows * P, W = (long long)cols * P;
+    const int n_bits = rows * cols;
+    for (int w = lane; w < words_per_item; w += 32) {
+      uint32_t word = 0;
+      for (int k = 0; k < nb; ++k) {
+        const int64_t* b = bboxes + ((long long)e * max_boxes + k) * 4;
+        const long long x1 = b[0], y1 = b[1], x2 = b[2], y2 = b[3];
+        long long px_lo, px_hi, py_lo, py_hi;  // inclusive candidate patch range
+        long long cpx = -1, cpy = -1;          // centre patch (rule 1)
+        if (rule == 0) {
+          const long long x1c = lmin(lmax(x1, 0), W), x2c = lmin(lmax(x2 + 1, 0), W);
+          const long long y1c = lmin(lmax(y1, 0), H), y2c = lmin(lmax(y2 + 1, 0), H);
+          if (x1c >= x2c || y1c >= y2c) continue;
+          px_lo = x1c / P; px_hi = (x2c - 1) / P; py_lo = y1c / P; py_hi = (y2c - 1) / P;
+        } else {
+          px_lo = floordiv(x1, P); px_hi = floordiv(x2, P); py_lo = floordiv(y1, P); py_hi = floordiv(y2, P);
+          cpx = floordiv(floordiv(x1 + x2, 2), P); cpy = floordiv(floordiv(y1 + y2, 2), P);
+        }
+        for (int bit = 0; bit < 32; ++bit) {
+          const int idx = w * 32 + bit;
+          if (idx >= n_bits) break;
+          const int y = idx / cols, x = idx - y * cols;
+          bool hit;
+          if (rule == 0) {
+            hit = (x >= px_lo && x <= px_hi && y >= py_lo && y <= py_hi);
+          } else {
+            hit = (x == cpx && y == cpy);
+            if (!hit && x >= px_lo && x <= px_hi && y >= py_lo && y <= py_hi) {
+              const long long oh = lmin((long long)(y + 1) * P, y2) - lmax((long long)y * P, y1);
+              const long long ow = lmin((long long)(x + 1) * P, x2) - lmax((long long)x * P, x1);
+              hit = 20 * (oh * ow) > (long long)P * P;
+            }
+          }
+          if (hit) word |= 1u << bit;
+        }
+      }
+      out[(long long)e * words_per_item + w] = word;
+    }
+  }
+}
+
+__global__ void bitmap_unpack_kernel(const uint32_t* __restrict__ words, int n, int bits_per_item, int words_per_item,
+                                     uint8_t* __restrict__ out) {
+  const long long total = (long long)n * bits_per_item;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i / bits_per_item), bit = (int)(i - (long long)e * bits_per_item);
+    out[i] = (words[(long long)e * words_per_item + (bit >> 5)] >> (bit & 31)) & 1u;
+  }
+}
+
+// parse_bboxes (general_env.py:381-504) in closed form: box k contributes to every patch of
+// [x1//P .. x2//P] x [y1//P .. y2//P] its intersection with that patch, in local inclusive
+// coordinates.  One thread per (episode, patch, box).  Degenerate boxes (x2 < x1 or y2 < y1)
+// follow the recursion's behaviour: only the top-left patch is written, un-clamped below.
+__global__ void split_boxes_kernel(const int64_t* __restrict__ bboxes, int n, int max_boxes, int P, int rows, int cols,
+                                   int64_t* __restrict__ local, uint8_t* __restrict__ present,
+                                   int32_t* __restrict__ status) {
+  const long long total = (long long)n * rows * cols * max_boxes;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % max_boxes);
+    long long t = i / max_boxes;
+    const int x = (int)(t % cols); t /= cols;
+    const int y = (int)(t % rows);
+    const int e = (int)(t / rows);
+    const int64_t* b = bboxes + ((long long)e * max_boxes + k) * 4;
+    // `.int()` truncation of the reference is a no-op for int64 inputs in range
+    const long long x1 = b[0], y1 = b[1], x2 = b[2], y2 = b[3];
+    const long long px1 = floordiv(x1, P), py1 = floordiv(y1, P);
+    const long long px2 = lmax(floordiv(x2, P), px1), py2 = lmax(floordiv(y2, P), py1);
+    if (px1 < 0 || py1 < 0 || px2 >= cols || py2 >= rows) {
+      if (status && x == 0 && y == 0) atomicOr(status, 4);
+    }
+    int64_t* o = local + i * 4;
+    const bool hit = (x >= px1 && x <= px2 && y >= py1 && y <= py2);
+    if (hit) {
+      const long long ox = (long long)x * P, oy = (long long)y * P;
+      o[0] = lmax(x1, ox) - ox;
+      o[1] = lmax(y1, oy) - oy;
+      o[2] = lmin(x2 - ox, (long long)P - 1);
+      o[3] = lmin(y2 - oy, (long long)P - 1);
+    } else {
+      o[0] = o[1] = o[2] = o[3] = 0;
+    }
+    present[i] = hit ? 1 : 0;
+  }
+}
+
+// local_bboxes (simple_env.py:231-268): one thread per (item, box).
+__global__ void local_boxes_kernel(const int64_t* __restrict__ bboxes, const int32_t* __restrict__ n_boxes,
+                                   int max_boxes, int P, const int64_t* __restrict__ positions,
+                                   const int32_t* __restrict__ src_index, int n_items, float* __restrict__ out) {
+  const long long total = (long long)n_items * max_boxes;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int item = (int)(i / max_boxes), k = (int)(i - (long long)item * max_boxes);
+    float* o = out + i * 6;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f;
+    const int e = src_index ? src_index[item] : item;
+    if (e >= 0 && k < (n_boxes ? n_boxes[e] : max_boxes)) {
+      const int64_t* b = bboxes + ((long long)e * max_boxes + k) * 4;
+      const long long px1 = positions[2 * (long long)item + 1] * P, py1 = positions[2 * (long long)item] * P;
+      const long long px2 = px1 + P, py2 = py1 + P;
+      const long long x1 = lmax(px1, b[0]), y1 = lmax(py1, b[1]);
+      const long long x2 = lmin(px2, b[2]), y2 = lmin(py2, b[3]);
+      if (x1 < x2 && y1 < y2) {  // the px1 <= x1 and x2 <= px2 halves hold by construction
+        v1 = (float)(x1 - px1); v2 = (float)(y1 - py1); v3 = (float)(x2 - px1); v4 = (float)(y2 - py1); v5 = 1.f;
+      }
+    }
+    o[0] = v0; o[1] = v1; o[2] = v2; o[3] = v3; o[4] = v4; o[5] = v5;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: reset / step / props -- one warp per episode
+// ------------------------------------------------------------------------------------------
+__global__ void env_reset_kernel(const int64_t* __restrict__ positions, uint32_t* __restrict__ visited,
+                                 int64_t* __restrict__ steps, uint8_t* __restrict__ has_stopped, int n, int rows,
+                                 int cols, int words, int32_t* __restrict__ status) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int e = blockIdx.x * warps_per_block + (threadIdx.x >> 5); e < n; e += gridDim.x * warps_per_block) {
+    const long long y = positions[2 * (long long)e], x = positions[2 * (long long)e + 1];
+    const bool ok = (y >= 0 && y < rows && x >= 0 && x < cols);
+    const int bit = ok ? (int)(y * cols + x) : -1;
+    for (int w = lane; w < words; w += 32)
+      visited[(long long)e * words + w] = (bit >= 0 && (bit >> 5) == w) ? (1u << (bit & 31)) : 0u;
+    if (lane == 0) {
+      steps[e] = 0;
+      has_stopped[e] = 0;
+      if (!ok && status) atomicOr(status, 1);
+    }
+  }
+}
+
+__global__ void env_step_kernel(const int64_t* __restrict__ pos_in, const int64_t* __restrict__ actions,
+                                int64_t* __restrict__ pos_out, uint32_t* __restrict__ visited,
+                                const uint32_t* __restrict__ bbox, int64_t* __restrict__ steps,
+                                uint8_t* __restrict__ has_stopped, float* __restrict__ rewards,
+                                uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, int n, int rows,
+                                int cols, int words, int max_ep_len, float cost, int stop_enabled,
+                                int32_t* __restrict__ status) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int e = blockIdx.x * warps_per_block + (threadIdx.x >> 5); e < n; e += gridDim.x * warps_per_block) {
+    // --- move + clamp, sticky stop (general_env.py:209-233); all lanes compute the same scalars
+    long long a = actions[e];
+    if (a < 0 || a > kStop) {
+      if (lane == 0 && status) atomicOr(status, 2);
+      a = kStop;  // invalid code: no move (flagged); the reference raises ValueError here
+    }
+    long long y = pos_in[2 * (long long)e] + kActionDy[a];
+    long long x = pos_in[2 * (long long)e + 1] + kActionDx[a];
+    y = lmin(lmax(y, 0), rows - 1);
+    x = lmin(lmax(x, 0), cols - 1);
+    const bool stopped = (has_stopped[e] != 0) || (a == kStop && actions[e] == kStop);
+    const int bit = (int)(y * cols + x);
+    // --- bitmaps: lane l owns words l, l+32, ...
+    int found = 0, every = 0, missing_after = 0;
+    bool fresh_here = false;
+    for (int w = lane; w < words; w += 32) {
+      const uint32_t v = visited[(long long)e * words + w];
+      const uint32_t b = bbox[(long long)e * words + w];
+      found += __popc(v & b);  // counts use the map BEFORE marking (general_env.py:347)
+      every += __popc(b);
+      uint32_t v_new = v;
+      if ((bit >> 5) == w) {
+        const uint32_t m = 1u << (bit & 31);
+        fresh_here = (b & m) != 0 && (v & m) == 0;
+        v_new = v | m;
+        visited[(long long)e * words + w] = v_new;
+      }
+      missing_after += __popc(b & ~v_new);
+    }
+    found = warp_sum(found);
+    every = warp_sum(every);
+    missing_after = warp_sum(missing_after);
+    const bool fresh = __any_sync(kFullMask, fresh_here);
+    if (lane == 0) {
+      // reward = fl32(fl32(fresh + cost) + stop_eval), general_env.py:334-358
+      float r = __fadd_rn(fresh ? 1.0f : 0.0f, cost);
+      if (stop_enabled) {
+        const int stop_eval = stopped ? (found == every ? found : found - every) : 0;
+        r = __fadd_rn(r, (float)stop_eval);
+      }
+      rewards[e] = r;
+      const long long s = steps[e] + 1;
+      steps[e] = s;
+      has_stopped[e] = stopped ? 1 : 0;
+      truncated[e] = s >= max_ep_len ? 1 : 0;
+      terminated[e] = stop_enabled ? (stopped ? 1 : 0) : (missing_after == 0 ? 1 : 0);
+      pos_out[2 * (long long)e] = y;
+      pos_out[2 * (long long)e + 1] = x;
+    }
+  }
+}
+
+__global__ void env_props_kernel(const uint32_t* __restrict__ visited, const uint32_t* __restrict__ bbox,
+                                 const uint8_t* __restrict__ has_stopped, int n, int words, int stop_enabled,
+                                 float* __restrict__ prop_patches, uint8_t* __restrict__ terminated) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int e = blockIdx.x * warps_per_block + (threadIdx.x >> 5); e < n; e += gridDim.x * warps_per_block) {
+    int found = 0, every = 0;
+    for (int w = lane; w < words; w += 32) {
+      const uint32_t v = visited[(long long)e * words + w], b = bbox[(long long)e * words + w];
+      found += __popc(v & b);
+      every += __popc(b);
+    }
+    found = warp_sum(found);
+    every = warp_sum(every);
+    if (lane == 0) {
+      // int64 / int64 true division in torch -> float32 operands (general_env.py:308-315)
+      if (prop_patches) prop_patches[e] = __fdiv_rn((float)found, (float)(every == 0 ? 1 : every));
+      if (terminated) terminated[e] = stop_enabled ? has_stopped[e] : (found == every ? 1 : 0);
+    }
+  }
+}
+
+}  // namespace jnk

@@ -1,0 +1,200 @@
+// K3 -- segmented scans: per-episode returns and supervised trajectory expansion.
+#pragma once
+
+#include "jn_device.cuh"
+
+namespace jnk {
+
+// ------------------------------------------------------------------------------------------
+// returns (reinforce.py:186-202)
+// ------------------------------------------------------------------------------------------
+// One thread per episode, reading the step-major [T, n] buffers the env wrote (coalesced
+// across the warp) and producing the reference's episode-major tensors.  The scan runs from
+// the last step backwards with a float64 accumulator that is rounded to float32 once per
+// element -- the arithmetic of torch's CPU cumsum on the flipped, masked rewards.  The order
+// of additions is the reference's, so the result is bit-identical, not merely close.
+__global__ void returns_kernel(const float* __restrict__ rewards_tn, const uint8_t* __restrict__ terminated_tn, int T,
+                               int n, float* __restrict__ rewards_out, uint8_t* __restrict__ masks,
+                               uint8_t* __restrict__ logit_masks, float* __restrict__ returns) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double acc = 0.0;
+  for (int t = T - 1; t >= 0; --t) {
+    const float r = rewards_tn[(long long)t * n + e];
+    // logit_masks[:, t] = masks[:, t]: column 0 is True, column t = !terminated after step t-1
+    const uint8_t alive = (t == 0) ? 1 : (terminated_tn[(long long)(t - 1) * n + e] ? 0 : 1);
+    const float term = __fmul_rn(r, alive ? 1.0f : 0.0f);  // fp32 product first (keeps -0.0 / NaN behaviour)
+    acc += (double)term;
+    returns[(long long)e * T + t] = (float)acc;
+    rewards_out[(long long)e * T + t] = r;
+    logit_masks[(long long)e * T + t] = alive;
+    masks[(long long)e * (T + 1) + t + 1] = terminated_tn[(long long)t * n + e] ? 0 : 1;
+  }
+  masks[(long long)e * (T + 1)] = 1;
+}
+
+__global__ void returns_rows_kernel(const float* __restrict__ rewards, long long r_stride,
+                                    const uint8_t* __restrict__ logit_masks, long long m_stride, int T, int n,
+                                    float* __restrict__ returns) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double acc = 0.0;
+  for (int t = T - 1; t >= 0; --t) {
+    const float term = __fmul_rn(rewards[e * r_stride + t], logit_masks[e * m_stride + t] ? 1.0f : 0.0f);
+    acc += (double)term;
+    returns[(long long)e * T + t] = (float)acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// trajectory expansion (simple_env.py:481-664)
+// ------------------------------------------------------------------------------------------
+// One warp per episode.  The host planner supplies the key points in visiting order as
+// segments (walk to `to`, best action points at `tgt`) and the pre-drawn replacement moves.
+//
+//   phase 1  lanes = segments: length L_k = Chebyshev distance from the previous end point,
+//            number of replacement draws the segment consumes (one if the group's opening
+//            "best action" is STOP, one if the walk passes over `tgt`), warp scans of both.
+//   phase 2  lanes = records: record t >= 1 belongs to the segment with pre_k < t <= pre_k+L_k;
+//            its position is closed form, start + sign(d) * min(j, |d|) per axis.
+//   phase 3  tail truncation: with ep_len > T only records [ep_len - T, ep_len) are kept.
+//
+// Segment tables live in shared memory (kMaxSeg per warp); episodes with more segments than
+// that raise status bit 8 and are left masked out.
+constexpr int kMaxSeg = 128;
+constexpr int kTrajWarps = 4;
+
+struct SegTable {
+  int16_t ay[kMaxSeg], ax[kMaxSeg];  // start of the walk
+  int16_t by[kMaxSeg], bx[kMaxSeg];  // end of the walk (to_visit)
+  int16_t ty[kMaxSeg], tx[kMaxSeg];  // true target
+  int32_t pre[kMaxSeg];              // records before this segment's first step, minus the start record
+  int32_t len[kMaxSeg];
+  int32_t draw0[kMaxSeg];            // first draw index of the segment
+  int16_t hit[kMaxSeg];              // step j (1-based) at which the walk stands on tgt, 0 = never
+  uint8_t first[kMaxSeg];            // opens a keypoint group
+  uint8_t open_draw[kMaxSeg];        // the group-opening best action is STOP (consumes draw0)
+};
+
+__device__ __forceinline__ int sgn(int v) { return (v > 0) - (v < 0); }
+
+__global__ void __launch_bounds__(kTrajWarps * 32)
+traj_expand_kernel(const int32_t* __restrict__ start_yx, const int32_t* __restrict__ seg_begin,
+                   const int32_t* __restrict__ seg_to, const int32_t* __restrict__ seg_tgt,
+                   const uint8_t* __restrict__ seg_flags, const int32_t* __restrict__ draw_begin,
+                   const uint8_t* __restrict__ draws, const uint32_t* __restrict__ area, int words_per_item,
+                   const int32_t* __restrict__ cols_arr, int n, int T, int64_t* __restrict__ positions,
+                   int64_t* __restrict__ cur_act, int64_t* __restrict__ next_act, int64_t* __restrict__ labels,
+                   float* __restrict__ masks, int32_t* __restrict__ gather_src, int32_t* __restrict__ ep_len_out,
+                   int32_t* __restrict__ status) {
+  __shared__ SegTable tables[kTrajWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  SegTable& s = tables[warp];
+  for (int e = blockIdx.x * kTrajWarps + warp; e < n; e += gridDim.x * kTrajWarps) {
+    const int s0 = seg_begin[e], ns = seg_begin[e + 1] - s0;
+    const int d0 = draw_begin[e], nd = draw_begin[e + 1] - d0;
+    const int sy = start_yx[2 * e], sx = start_yx[2 * e + 1];
+    const int cols = cols_arr[e];
+    const uint32_t* bm = area + (long long)e * words_per_item;
+    const long long o = (long long)e * T;
+    bool bad = ns > kMaxSeg;
+    int ep_len = 1;
+
+    if (!bad) {
+      // ---- phase 1: per-segment lengths and draw counts, scanned in blocks of 32 segments
+      int run_len = 0, run_draw = 0;
+      for (int base = 0; base < ns; base += 32) {
+        const int k = base + lane;
+        int L = 0, dcount = 0, hit = 0, ay = 0, ax = 0, by = 0, bx = 0, ty = 0, tx = 0, first = 0, open_draw = 0;
+        if (k < ns) {
+          by = seg_to[2 * (s0 + k)]; bx = seg_to[2 * (s0 + k) + 1];
+          ty = seg_tgt[2 * (s0 + k)]; tx = seg_tgt[2 * (s0 + k) + 1];
+          if (k == 0) { ay = sy; ax = sx; } else { ay = seg_to[2 * (s0 + k - 1)]; ax = seg_to[2 * (s0 + k - 1) + 1]; }
+          first = seg_flags[s0 + k] & 1;
+          const int dy = by - ay, dx = bx - ax;
+          L = imax(iabs(dy), iabs(dx));
+          open_draw = (first && ay == ty && ax == tx) ? 1 : 0;
+          // the walk stands on tgt at step j iff both axes agree; positions are monotone per axis
+          for (int j = 1; j <= L; ++j) {
+            const int py = ay + sgn(dy) * imin(j, iabs(dy)), px = ax + sgn(dx) * imin(j, iabs(dx));
+            if (py == ty && px == tx) { hit = j; break; }
+          }
+          dcount = open_draw + (hit ? 1 : 0);
+        }
+        // inclusive warp scans
+        int incl_len = L, incl_draw = dcount;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int a = __shfl_up_sync(0xffffffffu, incl_len, off), b = __shfl_up_sync(0xffffffffu, incl_draw, off);
+          if (lane >= off) { incl_len += a; incl_draw += b; }
+        }
+        if (k < ns) {
+          s.ay[k] = (int16_t)ay; s.ax[k] = (int16_t)ax; s.by[k] = (int16_t)by; s.bx[k] = (int16_t)bx;
+          s.ty[k] = (int16_t)ty; s.tx[k] = (int16_t)tx;
+          s.len[k] = L; s.pre[k] = run_len + incl_len - L;
+          s.draw0[k] = run_draw + incl_draw - dcount;
+          s.hit[k] = (int16_t)hit; s.first[k] = (uint8_t)first; s.open_draw[k] = (uint8_t)open_draw;
+        }
+        run_len += __shfl_sync(0xffffffffu, incl_len, 31);
+        run_draw += __shfl_sync(0xffffffffu, incl_draw, 31);
+      }
+      __syncwarp();
+      ep_len = 1 + run_len;
+      if (run_draw > nd) bad = true;  // planner supplied too few replacement moves
+    }
+    if (bad) {
+      if (lane == 0 && status) atomicOr(status, 8);
+      for (int t = lane; t < T; t += 32) {
+        positions[2 * (o + t)] = 0; positions[2 * (o + t) + 1] = 0;
+        cur_act[o + t] = 0; next_act[o + t] = 0; labels[o + t] = 0; masks[o + t] = 0.f; gather_src[o + t] = -1;
+      }
+      if (lane == 0) ep_len_out[e] = 0;
+      __syncwarp();
+      continue;
+    }
+
+    // ---- phases 2+3: one lane per kept record
+    const int drop = ep_len > T ? ep_len - T : 0;  // keep the LAST T records (simple_env.py:580-584)
+    for (int slot = lane; slot < T; slot += 32) {
+      const int t = slot + drop;  // record index in the untruncated episode
+      if (t >= ep_len) {
+        positions[2 * (o + slot)] = 0; positions[2 * (o + slot) + 1] = 0;
+        cur_act[o + slot] = 0; next_act[o + slot] = 0; labels[o + slot] = 0; masks[o + slot] = 0.f;
+        gather_src[o + slot] = -1;
+        continue;
+      }
+      int py = sy, px = sx, act = 0 /*LEFT placeholder, simple_env.py:527-534*/, best = 0;
+      // owning segment: records of segment k are t = pre_k + j, j = 1..len_k
+      // overwrite: the last group-opening segment with pre_k == t rewrites next_actions[t]
+      int own = -1, over = -1;
+      for (int k = 0; k < ns; ++k) {
+        const int pre = s.pre[k];
+        if (t > pre && t <= pre + s.len[k]) own = k;
+        if (s.first[k] && pre == t) over = k;
+      }
+      if (own >= 0) {
+        const int j = t - s.pre[own];
+        const int dy = s.by[own] - s.ay[own], dx = s.bx[own] - s.ax[own];
+        const int qy = s.ay[own] + sgn(dy) * imin(j - 1, iabs(dy)), qx = s.ax[own] + sgn(dx) * imin(j - 1, iabs(dx));
+        py = s.ay[own] + sgn(dy) * imin(j, iabs(dy)); px = s.ax[own] + sgn(dx) * imin(j, iabs(dx));
+        act = direction_code(s.by[own] - qy, s.bx[own] - qx);
+        best = direction_code(s.ty[own] - py, s.tx[own] - px);
+        if (best == kStop) best = draws[d0 + s.draw0[own] + s.open_draw[own]];  // j == hit[own]
+      }
+      if (over >= 0) {
+        best = direction_code(s.ty[over] - s.ay[over], s.tx[over] - s.ax[over]);
+        if (best == kStop) best = draws[d0 + s.draw0[over]];
+      }
+      const int bit = py * cols + px;
+      positions[2 * (o + slot)] = py; positions[2 * (o + slot) + 1] = px;
+      cur_act[o + slot] = act; next_act[o + slot] = best;
+      labels[o + slot] = (bm[bit >> 5] >> (bit & 31)) & 1u;
+      masks[o + slot] = 1.0f;
+      gather_src[o + slot] = e;
+    }
+    if (lane == 0) ep_len_out[e] = ep_len;
+    __syncwarp();
+  }
+}
+
+}  // namespace jnk

@@ -1,0 +1,282 @@
+"""Batched RL gaze environment on B200 -- drop-in for the reference's ``NeedleGeneralEnv``
+(``src/env/general_env.py:14-573``): same constructor, ``reset`` / ``step`` signatures, return
+values, attributes and quirks; the work is done by the CUDA kernels behind
+``include/jolineedle_b200.h`` (K0 overlap bitmaps, K1 glimpse gather, K2 warp-per-episode step).
+
+State layout in HBM (per episode): position int64[2]; visited / bbox bitmaps as uint32 words
+(bit = y*cols + x); steps int64; has_stopped u8.  The ``[B, rows, cols]`` bool tensors the
+reference exposes (``bbox_masks``, ``visited_patches``) are materialised on demand.
+
+Extensions (keyword-only, default = reference behaviour):
+  normalize  uint8 images -> float32 crops equal to ``ToTensor`` then crop (dataset.py:240)
+  focus      crops come out in the YOLOX Focus layout ``[4C, P/2, P/2]``
+  history    pre-allocate ``[B, max_ep_len + 1, C, P, P]`` and write step t's crops into slot
+             t + 1 (``patch_history(t)`` then replaces the caller's per-step ``torch.concat``,
+             reinforce.py:175-179)
+  device     upload CPU inputs to this CUDA device (the reference keeps everything on
+             ``images.device``; there is no CPU path here)
+"""
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from .. import _cabi
+from ..gather import ImageSet
+from .common import Action, ACTION_DELTAS  # noqa: F401  (re-exported like the reference module)
+
+
+class NeedleGeneralEnv:
+    def __init__(
+        self,
+        images: Tensor,
+        bboxes: Tensor,
+        patch_size: int,
+        max_ep_len: int,
+        n_glimps_levels: int,
+        stop_enabled: bool = False,
+        *,
+        normalize: bool = False,
+        focus: bool = False,
+        history: bool = False,
+        engine: str = "auto",
+        device=None,
+    ):
+        # same preconditions as general_env.py:37-39,50-51
+        assert images.shape[0] == bboxes.shape[0]
+        assert len(images.shape) == 4
+        assert n_glimps_levels > 0
+        if n_glimps_levels != 1:
+            raise NotImplementedError(
+                "n_glimps_levels > 1 (the zoomed-out glimpse pyramid, general_env.py:84-115) is not built; "
+                "every caller in the reference pins it to 1 (reinforce.py:58)"
+            )
+        if device is not None and not images.is_cuda:
+            images = images.to(device, non_blocking=True)
+        _cabi.require_cuda(images, "images")
+        self.patch_size = patch_size
+        self.max_ep_len = max_ep_len
+        self.n_glimps_levels = n_glimps_levels
+        self.stop_enabled = stop_enabled
+        self.batch_size, self.n_channels, self.height, self.width = images.shape
+        assert self.height % self.patch_size == 0
+        assert self.width % self.patch_size == 0
+        self.n_vertical_patches = self.height // self.patch_size
+        self.n_horizontal_patches = self.width // self.patch_size
+        self.device = images.device
+        self._normalize, self._focus, self._engine = normalize, focus, engine
+
+        self._set = ImageSet(images, patch_size)
+        # [B, G=1, C, H, W] view of the caller's tensor (callers read env.images[0, 0])
+        self.images = self._set._slabs[0].unsqueeze(1)
+        self.bboxes = bboxes
+        self._boxes_dev = bboxes.to(device=self.device, dtype=torch.int64).contiguous()
+        self._words = (self.n_vertical_patches * self.n_horizontal_patches + 31) // 32
+        self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._cost = float(torch.tensor(-1 / self.max_ep_len, dtype=torch.float32))  # fl32(-1/T), general_env.py:340
+        self._lib = _cabi.lib()
+
+        # K0: patch x bbox containment (any-pixel rule), general_env.py:75,360-379
+        self._bbox_words = torch.empty((self.batch_size, self._words), dtype=torch.int32, device=self.device)
+        n_boxes = self._boxes_dev.shape[1]
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.jn_patch_bitmaps(
+                self._boxes_dev.data_ptr(), None, self.batch_size, n_boxes, patch_size, self.n_vertical_patches,
+                self.n_horizontal_patches, None, None, _cabi.RULE_ANY_PIXEL, self._bbox_words.data_ptr(),
+                self._words, self._stream()))
+
+        self._history: Optional[Tensor] = None
+        if history:
+            self._history = torch.empty(
+                (self.batch_size, max_ep_len + 1) + self._set.out_shape(1, focus)[1:],
+                dtype=self._set.out_dtype(normalize), device=self.device)
+        self._t = 0
+        self.init_env_variables()
+
+    # ------------------------------------------------------------------------------------
+    def _stream(self):
+        return _cabi.stream_ptr(self.device)
+
+    def _unpack(self, words: Tensor) -> Tensor:
+        out = torch.empty((self.batch_size, self.n_vertical_patches, self.n_horizontal_patches), dtype=torch.bool,
+                          device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.jn_bitmap_unpack(words.data_ptr(), self.batch_size, self.n_vertical_patches,
+                                                   self.n_horizontal_patches, out.data_ptr(), self._stream()))
+        return out
+
+    @property
+    def bbox_masks(self) -> Tensor:
+        """``[B, rows, cols]`` bool: patch holds at least one box pixel (general_env.py:360-379)."""
+        return self._unpack(self._bbox_words)
+
+    @property
+    def visited_patches(self) -> Tensor:
+        return self._unpack(self._visited_words)
+
+    def init_env_variables(self):  # general_env.py:117-142
+        b, dev = self.batch_size, self.device
+        self.positions = torch.zeros((b, 2), dtype=torch.long, device=dev)
+        self._visited_words = torch.zeros((b, self._words), dtype=torch.int32, device=dev)
+        self.steps = torch.zeros((b,), dtype=torch.long, device=dev)
+        self.has_stopped = torch.zeros((b,), dtype=torch.bool, device=dev)
+        self._t = 0
+
+    def check_status(self):
+        """Synchronise and raise if a kernel flagged invalid input (the reference raises at the
+        call site; the kernels cannot, so they record it)."""
+        flags = int(self._status.item())
+        if flags & _cabi.STATUS_BAD_POSITION:
+            raise IndexError("a position was outside the patch grid")
+        if flags & _cabi.STATUS_BAD_ACTION:
+            raise ValueError("an action code was outside [0, 8]")
+        if flags & _cabi.STATUS_BAD_BOX:
+            raise IndexError("a bounding box falls outside the patch grid")
+
+    # ------------------------------------------------------------------------------------
+    def _gather(self) -> Tensor:
+        out = None
+        if self._history is not None:
+            out = self._history[:, self._t]
+        patches = self._set.gather(self.positions, out=out, normalize=self._normalize, focus=self._focus,
+                                   engine=self._engine, status=self._status)
+        return patches.unsqueeze(1)  # [B, G=1, C, P, P]
+
+    @property
+    def patches(self) -> Tensor:  # general_env.py:285-306
+        return self._gather()
+
+    def patch_history(self, upto: Optional[int] = None) -> Tensor:
+        """``[B, t+1, C, P, P]`` view of every crop produced so far (needs ``history=True``)."""
+        if self._history is None:
+            raise RuntimeError("construct the env with history=True to keep the crop history")
+        return self._history[:, : (self._t if upto is None else upto) + 1]
+
+    def reset(self, positions: Optional[Tensor] = None) -> Tuple[Tensor, dict]:  # general_env.py:144-170
+        self.init_env_variables()
+        if positions is not None:
+            self.positions = positions.to(device=self.device, dtype=torch.long).contiguous()
+        else:
+            # host RNG in the reference's order: rows first, then columns, CPU default generator
+            ys = torch.randint(low=0, high=self.n_vertical_patches, size=(self.batch_size,))
+            xs = torch.randint(low=0, high=self.n_horizontal_patches, size=(self.batch_size,))
+            self.positions = torch.stack((ys, xs), dim=1).to(self.device, non_blocking=True)
+        assert tuple(self.positions.shape) == (self.batch_size, 2)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.jn_env_reset(
+                self.positions.data_ptr(), self._visited_words.data_ptr(), self.steps.data_ptr(),
+                self.has_stopped.data_ptr(), self.batch_size, self.n_vertical_patches, self.n_horizontal_patches,
+                self._status.data_ptr(), self._stream()))
+        infos = {"positions": self.positions}
+        return self._gather(), infos
+
+    @torch.no_grad()
+    def step(self, actions: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor, dict]:  # general_env.py:172-207
+        b, dev = self.batch_size, self.device
+        actions = actions.to(device=dev, dtype=torch.long).contiguous()
+        assert actions.numel() == b
+        new_positions = torch.empty((b, 2), dtype=torch.long, device=dev)
+        rewards = torch.empty((b,), dtype=torch.float32, device=dev)
+        terminated = torch.empty((b,), dtype=torch.bool, device=dev)
+        truncated = torch.empty((b,), dtype=torch.bool, device=dev)
+        with torch.cuda.device(dev):
+            _cabi.check(self._lib.jn_env_step(
+                self.positions.data_ptr(), actions.data_ptr(), new_positions.data_ptr(),
+                self._visited_words.data_ptr(), self._bbox_words.data_ptr(), self.steps.data_ptr(),
+                self.has_stopped.data_ptr(), rewards.data_ptr(), terminated.data_ptr(), truncated.data_ptr(), b,
+                self.n_vertical_patches, self.n_horizontal_patches, self.max_ep_len, self._cost,
+                1 if self.stop_enabled else 0, self._status.data_ptr(), self._stream()))
+        self.positions = new_positions
+        self._t += 1
+        infos = {"positions": self.positions}
+        return self._gather(), rewards, terminated, truncated, infos
+
+    # ------------------------------------------------------------------------------------
+    def _props(self, want_prop: bool, want_term: bool):
+        prop = torch.empty((self.batch_size,), dtype=torch.float32, device=self.device) if want_prop else None
+        term = torch.empty((self.batch_size,), dtype=torch.bool, device=self.device) if want_term else None
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.jn_env_props(
+                self._visited_words.data_ptr(), self._bbox_words.data_ptr(), self.has_stopped.data_ptr(),
+                self.batch_size, self.n_vertical_patches, self.n_horizontal_patches, 1 if self.stop_enabled else 0,
+                _cabi.ptr(prop), _cabi.ptr(term), self._stream()))
+        return prop, term
+
+    @property
+    def terminated(self) -> Tensor:  # general_env.py:235-246
+        return self._props(False, True)[1]
+
+    @property
+    def prop_patches_found(self) -> Tensor:  # general_env.py:308-315
+        return self._props(True, False)[0]
+
+    @property
+    def prop_bboxes_found(self) -> Tensor:  # general_env.py:317-319
+        return (self.prop_patches_found > 0).to(torch.float32)
+
+    @property
+    def tiles_reached(self) -> Tensor:  # general_env.py:248-283
+        hot = torch.zeros((self.batch_size, self.n_vertical_patches, self.n_horizontal_patches), dtype=torch.bool,
+                          device=self.device)
+        hot[torch.arange(self.batch_size, device=self.device), self.positions[:, 0], self.positions[:, 1]] = True
+        return hot
+
+    # ------------------------------------------------------------------------------------
+    # detection side (general_env.py:381-573): K0 split table + host bookkeeping + K1 gather
+    def parse_bboxes(self, bboxes=None) -> Tuple[Tensor, Tensor]:
+        """``[B, rows, cols, N, 4]`` local boxes and ``[B, rows, cols, N]`` presence
+        (general_env.py:381-504)."""
+        boxes = self._boxes_dev if bboxes is None else torch.as_tensor(bboxes).to(self.device, torch.int64).contiguous()
+        b, n = boxes.shape[0], boxes.shape[1]
+        rows, cols = self.n_vertical_patches, self.n_horizontal_patches
+        local = torch.empty((b, rows, cols, n, 4), dtype=torch.long, device=self.device)
+        present = torch.empty((b, rows, cols, n), dtype=torch.bool, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.jn_split_boxes(boxes.data_ptr(), b, n, self.patch_size, rows, cols,
+                                                 local.data_ptr(), present.data_ptr(), self._status.data_ptr(),
+                                                 self._stream()))
+        return local, present
+
+    @torch.no_grad()
+    def get_detection_batch(self, sample_neg: int = 1):  # general_env.py:506-546
+        local, present = self.parse_bboxes()
+        present = present.squeeze(-1)  # only collapses when there is a single box per image (reference quirk)
+        present_host = present.cpu()
+        img_ids: List[int] = []
+        rows_ids: List[Tensor] = []
+        cols_ids: List[Tensor] = []
+        for i in range(self.batch_size):
+            hits = torch.where(present_host[i])
+            misses = torch.where(~present_host[i])
+            pick = torch.randperm(len(misses[0]))[:sample_neg]  # CPU generator, one draw per image
+            misses = tuple(m[pick] for m in misses)
+            r = torch.cat((hits[0], misses[0]))
+            c = torch.cat((hits[1], misses[1]))
+            rows_ids.append(r)
+            cols_ids.append(c)
+            img_ids.extend([i] * len(r))
+        r_all, c_all = torch.cat(rows_ids), torch.cat(cols_ids)
+        positions = torch.stack((r_all, c_all), dim=1).to(self.device)
+        src = torch.tensor(img_ids, dtype=torch.int32, device=self.device)
+        patches = self._set.gather(positions, src_index=src, engine=self._engine, status=self._status)
+        src_l = src.long()
+        boxes = local[src_l, positions[:, 0], positions[:, 1]]  # [n, N, 4]
+        boxes = torch.nn.functional.pad(boxes, (1, 0))  # class id 0 in front
+        return patches, boxes
+
+    @torch.no_grad()
+    def get_detection_targets(self) -> List[Tensor]:  # general_env.py:548-573
+        local, _ = self.parse_bboxes()
+        rows, cols, p = self.n_vertical_patches, self.n_horizontal_patches, self.patch_size
+        ys = torch.arange(rows, device=self.device).view(1, rows, 1, 1)
+        xs = torch.arange(cols, device=self.device).view(1, 1, cols, 1)
+        offset = torch.stack((xs.expand(1, rows, cols, 1), ys.expand(1, rows, cols, 1)) * 2, dim=-1) * p
+        glob = local + offset  # x1+ox, y1+oy, x2+ox, y2+oy
+        keep = local.abs().sum(dim=-1) != 0  # all-zero entries are skipped (general_env.py:560)
+        out = []
+        for i in range(self.batch_size):
+            sel = glob[i][keep[i]]  # row-major over (y, x, k): the reference's loop order
+            if sel.shape[0] == 0:
+                raise RuntimeError("stack expects a non-empty TensorList")  # what torch.stack([]) raises
+            out.append(torch.nn.functional.pad(sel, (1, 0)))
+        return out

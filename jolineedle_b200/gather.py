@@ -1,0 +1,112 @@
+"""Image sets and the glimpse gather (K1) -- thin Python handles over the C ABI.
+
+An :class:`ImageSet` borrows one ``[B, C, H, W]`` CUDA tensor, or a list of ``[C, H, W]`` /
+``[b, C, H, W]`` CUDA tensors of possibly different sizes, and serves ``[C, P, P]`` tiles out
+of them.  No pixel is copied at construction; the tensors are kept alive by the handle.
+"""
+import ctypes
+from typing import List, Optional, Sequence, Union
+
+import torch
+
+from . import _cabi
+
+
+class ImageSet:
+    def __init__(self, images: Union[torch.Tensor, Sequence[torch.Tensor]], patch_size: int):
+        slabs: List[torch.Tensor] = [images] if isinstance(images, torch.Tensor) else list(images)
+        if not slabs:
+            raise ValueError("empty image set")
+        norm = []
+        for t in slabs:
+            _cabi.require_cuda(t, "images")
+            if t.dim() == 3:
+                t = t.unsqueeze(0)
+            if t.dim() != 4:
+                raise ValueError(f"images must be [C,H,W] or [B,C,H,W], got shape {tuple(t.shape)}")
+            if not t.is_contiguous():
+                t = t.contiguous()
+            norm.append(t)
+        first = norm[0]
+        self.device, self.dtype, self.channels = first.device, first.dtype, first.shape[1]
+        for t in norm:
+            if t.device != self.device or t.dtype != self.dtype or t.shape[1] != self.channels:
+                raise ValueError("all images of a set must share device, dtype and channel count")
+        self.patch_size = int(patch_size)
+        self._slabs = norm  # keeps the memory alive
+        self.counts = [t.shape[0] for t in norm]
+        self.n_images = sum(self.counts)
+        self.heights = [t.shape[2] for t in norm]
+        self.widths = [t.shape[3] for t in norm]
+        n = len(norm)
+        ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in norm])
+        counts = (ctypes.c_int32 * n)(*self.counts)
+        heights = (ctypes.c_int32 * n)(*self.heights)
+        widths = (ctypes.c_int32 * n)(*self.widths)
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().jn_images_create(
+                ctypes.byref(handle), n, ptrs, counts, heights, widths, self.channels,
+                _cabi.dtype_code(self.dtype), self.patch_size, _cabi.stream_ptr(self.device),
+            )
+        # same precondition as the reference envs: sizes must be multiples of the patch size
+        _cabi.check(rc, invalid_exc=AssertionError)
+        self._handle = handle
+
+    def __del__(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h:
+            try:
+                _cabi.lib().jn_images_destroy(h)
+            except Exception:  # interpreter shutdown
+                pass
+
+    def engine_available(self, engine: str) -> bool:
+        return bool(_cabi.lib().jn_images_tma_ok(self._handle, _cabi.ENGINES[engine]))
+
+    def out_shape(self, n_items: int, focus: bool):
+        p, c = self.patch_size, self.channels
+        return (n_items, 4 * c, p // 2, p // 2) if focus else (n_items, c, p, p)
+
+    def out_dtype(self, normalize: bool) -> torch.dtype:
+        return torch.float32 if normalize else self.dtype
+
+    def gather(
+        self,
+        positions: torch.Tensor,
+        src_index: Optional[torch.Tensor] = None,
+        out: Optional[torch.Tensor] = None,
+        normalize: bool = False,
+        focus: bool = False,
+        engine: str = "auto",
+        status: Optional[torch.Tensor] = None,
+    ) -> torch.Tensor:
+        """Tile ``positions[i] = (y, x)`` of image ``src_index[i]`` (default ``i``; negative =
+        zeros) -> ``out[i]``.  ``out`` may be any tensor whose ``out[i]`` is contiguous (e.g. a
+        time slot ``history[:, t]`` of a ``[B, T, C, P, P]`` buffer)."""
+        _cabi.require_cuda(positions, "positions")
+        if positions.dtype != torch.int64 or positions.dim() != 2 or positions.shape[1] != 2:
+            raise ValueError("positions must be a LongTensor of shape [n, 2]")
+        positions = positions.contiguous()
+        n = positions.shape[0]
+        if src_index is not None:
+            if src_index.dtype != torch.int32 or src_index.numel() != n:
+                raise ValueError("src_index must be an int32 tensor with one entry per position")
+            src_index = src_index.contiguous()
+        shape, dtype = self.out_shape(n, focus), self.out_dtype(normalize)
+        if out is None:
+            out = torch.empty(shape, dtype=dtype, device=self.device)
+        else:
+            if tuple(out.shape) != shape or out.dtype != dtype or out.device != self.device:
+                raise ValueError(f"out must be {shape} {dtype} on {self.device}, got {tuple(out.shape)} {out.dtype}")
+            if n > 0 and not out[0].is_contiguous():
+                raise ValueError("out[i] must be contiguous")
+        flags = (_cabi.GATHER_NORMALIZE if normalize else 0) | (_cabi.GATHER_FOCUS if focus else 0)
+        stride = out.stride(0) * out.element_size() if n > 1 else out[0].numel() * out.element_size() if n else 0
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().jn_gather(
+                self._handle, positions.data_ptr(), _cabi.ptr(src_index), n, out.data_ptr(), stride, flags,
+                _cabi.ENGINES[engine], _cabi.ptr(status), _cabi.stream_ptr(self.device),
+            )
+        _cabi.check(rc)
+        return out

@@ -1,0 +1,139 @@
+"""K3a/K0/K1 parity of the supervised pipeline: golden fixtures of the reference and seeded
+comparisons against the oracle, through the product's public API."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, scenario, seed_python_random, simple_case, synth_u8, to_f32
+from oracle.traj_oracle import TrajectoryOracle, collate_oracle, generate_trajectories_oracle
+
+pytestmark = pytest.mark.gpu
+
+SAMPLE_KEYS = ("patches", "current_actions", "next_actions", "positions", "masks", "labels", "local_bboxes",
+               "patches_yolox", "bboxes_yolox")
+
+
+def bboxes_of(raw):
+    from jolineedle_b200.utils import BBox, Position
+
+    return [BBox(Position(y1, x1), Position(y2, x2)) for (x1, y1, x2, y2) in raw]
+
+
+def test_generate_sample_matches_reference_fixtures():
+    from jolineedle_b200.env.simple_env import NeedleSimpleEnv
+    from jolineedle_b200.utils import Position
+
+    fx = load_golden("simple_env.npz")
+    for name in fx["names"]:
+        c, cfg = simple_case(fx, str(name))
+        for variant in ("f32", "u8"):
+            seed_python_random(cfg["seed"])
+            img = to_f32(c["u8"]).cuda() if variant == "f32" else torch.from_numpy(c["u8"]).cuda()
+            env = NeedleSimpleEnv(img, cfg["P"], bboxes_of(c["raw_boxes"].tolist()), seed=cfg["seed"],
+                                  normalize=(variant == "u8"))
+            pos = None if cfg["position"] is None else Position(*cfg["position"])
+            s = env.generate_sample(cfg["T"], cfg["kmin"], cfg["kmax"], binomial_keypoints=cfg["binomial"], position=pos)
+            assert set(s) == set(SAMPLE_KEYS)
+            for k in SAMPLE_KEYS:
+                assert s[k].dtype == torch.from_numpy(c[k]).dtype, (name, k)
+                assert np.array_equal(s[k].cpu().numpy(), c[k]), (name, variant, k)
+
+
+def test_collate_and_batched_entry_match_reference_fixtures():
+    from jolineedle_b200.env.simple_env import NeedleSimpleEnv, generate_trajectories
+
+    fx = load_golden("simple_env.npz")
+    ref = scenario(fx, "collate")
+    members = fx["collate/members"].tolist()
+    # (a) per-env samples + collate_fn, exactly like the reference trainer
+    samples = []
+    for j, idx in enumerate(members):
+        c, cfg = simple_case(fx, f"s{idx:02d}")
+        seed_python_random(cfg["seed"])
+        env = NeedleSimpleEnv(to_f32(c["u8"]).cuda(), cfg["P"], bboxes_of(c["raw_boxes"].tolist()), seed=cfg["seed"])
+        from jolineedle_b200.utils import Position
+
+        pos = None if cfg["position"] is None else Position(*cfg["position"])
+        s = env.generate_sample(cfg["T"], cfg["kmin"], cfg["kmax"], binomial_keypoints=cfg["binomial"], position=pos)
+        s["class_id"] = torch.tensor(j, dtype=torch.long, device="cuda")
+        samples.append(s)
+    batch = NeedleSimpleEnv.collate_fn(samples)
+    assert set(batch) == set(ref)
+    for k, v in batch.items():
+        assert np.array_equal(v.cpu().numpy(), ref[k]), k
+
+
+@pytest.mark.parametrize("binomial", [False, True])
+@pytest.mark.parametrize("P,gh,gw,b,T", [(448, 5, 5, 4, 8), (64, 5, 6, 16, 8), (32, 9, 7, 8, 20)])
+def test_batched_trajectories_match_oracle(binomial, P, gh, gw, b, T):
+    """cfg 1 (2240x2240, P=448, T=8, B=4) and smaller-patch batches, seeded, against the oracle's
+    serial loop (supervised.py:116-136).  Images of one batch differ in size in the last case."""
+    from jolineedle_b200.env.simple_env import generate_trajectories
+
+    rng = np.random.default_rng(P + T + int(binomial))
+    images, boxes = [], []
+    for i in range(b):
+        gh_i, gw_i = (gh, gw) if P != 32 else (gh - i % 3, gw + i % 2)
+        h, w = gh_i * P, gw_i * P
+        images.append(to_f32(synth_u8(1, 3, h, w, salt=i)[0]))
+        raw = []
+        for _ in range(int(rng.integers(0, 4))):
+            bw, bh = (int(v) for v in rng.integers(4, P + P // 2, size=2))
+            x1, y1 = int(rng.integers(0, w - 4)), int(rng.integers(0, h - 4))
+            raw.append((x1, y1, min(x1 + bw, w - 1), min(y1 + bh, h - 1)))
+        boxes.append(raw)
+    seeds = [500 + i for i in range(b)]
+    class_ids = list(range(b))
+    random.seed(11)
+    want = generate_trajectories_oracle(images, [[((y1, x1), (y2, x2)) for (x1, y1, x2, y2) in r] for r in boxes],
+                                        class_ids, P, T, 0, 3, binomial, seeds=seeds)
+    random.seed(11)
+    got = generate_trajectories({"image": [im.cuda() for im in images], "bboxes": [bboxes_of(r) for r in boxes],
+                                 "class_id": class_ids}, P, T, 0, 3, binomial_keypoints=binomial, seeds=seeds)
+    assert set(got) == set(want)
+    for k in want:
+        assert got[k].dtype == want[k].dtype and tuple(got[k].shape) == tuple(want[k].shape), k
+        assert torch.equal(got[k].cpu(), want[k]), k
+
+
+def test_large_batch_properties_cfg2_shape():
+    """cfg 2 (B=256, 2240x2688, P=448, T=8, binomial key points 0-3) with uint8-resident images:
+    every recorded slot holds the crop at its recorded position, padded slots are zero, actions
+    are consistent with consecutive positions."""
+    from jolineedle_b200.env.simple_env import generate_trajectories
+
+    b, P, gh, gw, T = 256, 448, 5, 6, 8
+    g = torch.Generator(device="cuda").manual_seed(8)
+    base = torch.randint(0, 256, (16, 3, gh * P, gw * P), dtype=torch.uint8, device="cuda", generator=g)
+    rng = np.random.default_rng(21)
+    images = [base[i % 16] for i in range(b)]
+    boxes = []
+    for i in range(b):
+        raw = []
+        for _ in range(int(rng.integers(1, 4))):
+            bw, bh = (int(v) for v in rng.integers(8, 448, size=2))
+            x1, y1 = int(rng.integers(0, gw * P - bw)), int(rng.integers(0, gh * P - bh))
+            raw.append((x1, y1, x1 + bw, y1 + bh))
+        boxes.append(bboxes_of(raw))
+    out = generate_trajectories({"image": images, "bboxes": boxes, "class_id": [0] * b}, P, T, 0, 3,
+                                binomial_keypoints=True, seeds=list(range(b)), normalize=True)
+    assert tuple(out["patches"].shape) == (b, T, 3, P, P) and out["patches"].dtype == torch.float32
+    masks, pos = out["masks"].cpu(), out["positions"].cpu()
+    delta = torch.tensor([(0, -1), (0, 1), (-1, 0), (1, 0), (-1, -1), (-1, 1), (1, -1), (1, 1), (0, 0)])
+    assert bool(((masks == 0) | (masks == 1)).all()) and bool((masks[:, 0] == 1).all())
+    assert bool((masks[:, 1:] <= masks[:, :-1]).all())  # recorded slots form a prefix
+    cur = out["current_actions"].cpu()
+    for i in range(0, b, 7):
+        n = int(masks[i].sum())
+        for t in range(T):
+            if t < n:
+                y, x = pos[i, t].tolist()
+                want = images[i][:, y * P:(y + 1) * P, x * P:(x + 1) * P].float() / 255
+                assert torch.equal(out["patches"][i, t], want)
+                if t > 0:
+                    assert torch.equal(pos[i, t], pos[i, t - 1] + delta[cur[i, t]])
+            else:
+                assert float(out["patches"][i, t].abs().sum()) == 0.0
+    assert int(out["next_actions"].max()) <= 7  # STOP never appears as a best action
