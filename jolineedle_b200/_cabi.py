@@ -54,14 +54,43 @@ SIGNATURES = {
                                _P, _P, _P]),
 }
 
-_lib: Optional[ctypes.CDLL] = None
+# entry points that launch exactly one kernel of ours per successful call
+KERNEL_CALLS = frozenset({
+    "jn_gather", "jn_patch_bitmaps", "jn_bitmap_unpack", "jn_split_boxes", "jn_local_boxes", "jn_env_reset",
+    "jn_env_step", "jn_env_props", "jn_returns", "jn_returns_rows", "jn_traj_expand",
+})
+
+
+class _CountingLibrary:
+    """Attribute proxy over the CDLL that counts kernel-launching calls (bench.py reports the
+    number of our launches inside its timed region)."""
+
+    def __init__(self, handle: ctypes.CDLL):
+        self._handle = handle
+        self.launches = 0
+        for name in SIGNATURES:
+            fn = getattr(handle, name)
+            if name in KERNEL_CALLS:
+                setattr(self, name, self._counted(fn))
+            else:
+                setattr(self, name, fn)
+
+    def _counted(self, fn):
+        def call(*args):
+            self.launches += 1
+            return fn(*args)
+
+        return call
+
+
+_lib: Optional[_CountingLibrary] = None
 
 
 def library_path() -> str:
     return _LIB_PATH
 
 
-def lib() -> ctypes.CDLL:
+def lib() -> _CountingLibrary:
     """Load the shared object (once).  Raises ``NativeLibraryError`` when it is not built."""
     global _lib
     if _lib is None:
@@ -77,8 +106,13 @@ def lib() -> ctypes.CDLL:
             fn.argtypes = argtypes
         if handle.jn_abi_version() != 1:
             raise NativeLibraryError(f"ABI version mismatch: library reports {handle.jn_abi_version()}")
-        _lib = handle
+        _lib = _CountingLibrary(handle)
     return _lib
+
+
+def launch_count() -> int:
+    """Kernel launches issued through this binding since import."""
+    return lib().launches
 
 
 def check(rc: int, invalid_exc=ValueError):

@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -146,16 +147,39 @@ int encode_slab_map(CUtensorMap* map, const void* ptr, int elem, int n_planes, i
 
 namespace {
 
-constexpr int kCopyStages = 6, kCopyAhead = 3;
 constexpr int kXformStages = 4, kXformWarps = 8;
+
+// Pipeline shape of the gather kernels.  The defaults are the measured optimum on B200
+// (profiles/); JN_GATHER_TUNE="copy_stages,copy_ahead,copy_chunk_bytes,copy_ctas_per_sm,
+// xform_chunk_bytes,xform_ctas_per_sm" overrides them for tuning sweeps (0 keeps a default).
+struct GatherTune {
+  int copy_stages = 6, copy_ahead = 3, copy_chunk = 32768, copy_ctas = 0;
+  int xform_chunk = 0, xform_ctas = 0;
+};
+
+GatherTune gather_tune() {
+  GatherTune t;
+  if (const char* env = getenv("JN_GATHER_TUNE")) {
+    int v[6] = {0, 0, 0, 0, 0, 0};
+    sscanf(env, "%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]);
+    if (v[0] > 0) t.copy_stages = v[0];
+    if (v[1] > 0) t.copy_ahead = v[1];
+    if (v[2] > 0) t.copy_chunk = v[2];
+    if (v[3] > 0) t.copy_ctas = v[3];
+    if (v[4] > 0) t.xform_chunk = v[4];
+    if (v[5] > 0) t.xform_ctas = v[5];
+  }
+  return t;
+}
 
 template <typename Kernel>
 int launch_persistent(Kernel kernel, const jnk::GatherArgs& a, const CUtensorMap& map, int threads, size_t smem,
-                      const DeviceInfo& dev, cudaStream_t stream) {
+                      const DeviceInfo& dev, cudaStream_t stream, int ctas_cap = 0) {
   JN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   JN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
   if (per_sm < 1) return fail(JN_ERR_CUDA, "gather kernel does not fit on an SM (%zu bytes of shared memory)", smem);
+  if (ctas_cap > 0 && per_sm > ctas_cap) per_sm = ctas_cap;
   long long grid = (long long)dev.sm_count * per_sm;
   if (grid > a.total_chunks) grid = a.total_chunks;
   kernel<<<(int)grid, threads, smem, stream>>>(a, map);
@@ -320,7 +344,8 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
   }
 
   // TMA engines: chunk geometry
-  const int target = plain_copy ? 32768 : (set->elem == 4 ? 24576 : 16384);
+  const GatherTune tune = gather_tune();
+  const int target = plain_copy ? tune.copy_chunk : (tune.xform_chunk ? tune.xform_chunk : (set->elem == 4 ? 24576 : 16384));
   const int rows = pick_rows(P, set->elem, target, focus);
   JN_REQUIRE(rows > 0, "patch row of %d bytes does not fit a shared-memory stage", P * set->elem);
   a.rows = rows; a.chunks_per_plane = P / rows;
@@ -338,19 +363,25 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
   }
 
   if (plain_copy) {
-    const size_t smem = kCopyStages * chunk_bytes + jnk::kZeroBytes + kCopyStages * sizeof(uint64_t);
-    if (engine == JN_ENGINE_TENSOR)
-      return launch_persistent(jnk::gather_copy_kernel<kCopyStages, kCopyAhead, true>, a, map, 32, smem, dev, stream);
-    return launch_persistent(jnk::gather_copy_kernel<kCopyStages, kCopyAhead, false>, a, map, 32, smem, dev, stream);
+    const size_t smem = tune.copy_stages * chunk_bytes + jnk::kZeroBytes + tune.copy_stages * sizeof(uint64_t);
+    const bool tensor = engine == JN_ENGINE_TENSOR;
+#define JN_COPY(S, D)                                                                                              \
+  if (tune.copy_stages == S && tune.copy_ahead == D)                                                               \
+    return tensor ? launch_persistent(jnk::gather_copy_kernel<S, D, true>, a, map, 32, smem, dev, stream, tune.copy_ctas) \
+                  : launch_persistent(jnk::gather_copy_kernel<S, D, false>, a, map, 32, smem, dev, stream, tune.copy_ctas);
+    JN_COPY(6, 3) JN_COPY(4, 2) JN_COPY(3, 2) JN_COPY(6, 4) JN_COPY(8, 4) JN_COPY(8, 6) JN_COPY(12, 6) JN_COPY(12, 9)
+#undef JN_COPY
+    return fail(JN_ERR_INVALID, "JN_GATHER_TUNE: no copy kernel with %d stages / lookahead %d", tune.copy_stages,
+                tune.copy_ahead);
   }
   const size_t smem = kXformStages * chunk_bytes + 2 * kXformStages * sizeof(uint64_t);
   const int threads = (kXformWarps + 1) * 32;
   const bool tensor = engine == JN_ENGINE_TENSOR;
 #define JN_XFORM(mode)                                                                                           \
   (tensor ? launch_persistent(jnk::gather_xform_kernel<mode, kXformStages, kXformWarps, true>, a, map, threads, smem, \
-                              dev, stream)                                                                       \
+                              dev, stream, tune.xform_ctas)                                                      \
           : launch_persistent(jnk::gather_xform_kernel<mode, kXformStages, kXformWarps, false>, a, map, threads,  \
-                              smem, dev, stream))
+                              smem, dev, stream, tune.xform_ctas))
   if (normalize && !focus) return JN_XFORM(jnk::kNormPlain);
   if (normalize && focus) return JN_XFORM(jnk::kNormFocus);
   return JN_XFORM(jnk::kF32Focus);

@@ -139,7 +139,7 @@ class NeedleGeneralEnv:
         if self._history is not None:
             out = self._history[:, self._t]
         patches = self._set.gather(self.positions, out=out, normalize=self._normalize, focus=self._focus,
-                                   engine=self._engine, status=self._status)
+                                   engine=self._engine, status=self._status, tag="step")
         return patches.unsqueeze(1)  # [B, G=1, C, P, P]
 
     @property

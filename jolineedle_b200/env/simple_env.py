@@ -440,10 +440,10 @@ def expand_plans(
     # K1: the glimpses themselves, straight into [B, T, C, P, P]; padded slots are zero-filled
     image_set.gather(out["positions"].view(n * T, 2), src_index=gather_src.view(n * T),
                      out=out["patches"].view((n * T,) + out["patches"].shape[2:]), normalize=normalize,
-                     engine=engine, status=status)
+                     engine=engine, status=status, tag="trajectory")
     # detection patches: every box patch + one random empty patch per image (simple_env.py:397-441)
     out["patches_yolox"] = image_set.gather(d_det_pos, src_index=d_det_src, normalize=normalize, engine=engine,
-                                            status=status)
+                                            status=status, tag="detection")
     det_boxes = torch.empty((n_det, n_max, 6), dtype=torch.float32, device=dev)
     if n_max > 0 and n_det > 0:
         with torch.cuda.device(dev):

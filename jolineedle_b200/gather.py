@@ -11,6 +11,10 @@ import torch
 
 from . import _cabi
 
+# Optional per-launch timing of the gather (bench.py's roofline leg): when a list is installed
+# here, every gather appends (tag, n_items, start_event, end_event) recorded on the launch stream.
+TIMING: Optional[list] = None
+
 
 class ImageSet:
     def __init__(self, images: Union[torch.Tensor, Sequence[torch.Tensor]], patch_size: int):
@@ -80,6 +84,7 @@ class ImageSet:
         focus: bool = False,
         engine: str = "auto",
         status: Optional[torch.Tensor] = None,
+        tag: str = "",
     ) -> torch.Tensor:
         """Tile ``positions[i] = (y, x)`` of image ``src_index[i]`` (default ``i``; negative =
         zeros) -> ``out[i]``.  ``out`` may be any tensor whose ``out[i]`` is contiguous (e.g. a
@@ -103,10 +108,17 @@ class ImageSet:
                 raise ValueError("out[i] must be contiguous")
         flags = (_cabi.GATHER_NORMALIZE if normalize else 0) | (_cabi.GATHER_FOCUS if focus else 0)
         stride = out.stride(0) * out.element_size() if n > 1 else out[0].numel() * out.element_size() if n else 0
+        timing = TIMING
         with torch.cuda.device(self.device):
+            if timing is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
             rc = _cabi.lib().jn_gather(
                 self._handle, positions.data_ptr(), _cabi.ptr(src_index), n, out.data_ptr(), stride, flags,
                 _cabi.ENGINES[engine], _cabi.ptr(status), _cabi.stream_ptr(self.device),
             )
+            if timing is not None:
+                ev1.record()
+                timing.append((tag, n, ev0, ev1))
         _cabi.check(rc)
         return out

@@ -164,7 +164,10 @@ def test_full_size_round_trip_lard_shape(dtype, normalize):
     ys, xs, bs = torch.meshgrid(torch.arange(gh), torch.arange(gw), torch.arange(b), indexing="ij")
     pos = torch.stack([ys.flatten(), xs.flatten()], 1).cuda()
     src = bs.flatten().to(torch.int32).cuda()
-    want = imgs.float() / 255 if normalize else imgs
+    # NB: `x.float() / 255` on a CUDA tensor multiplies by a reciprocal; the reference's ToTensor divides on
+    # the CPU.  The 256-entry table (tests/golden/norm.npz, produced by torch CPU) is the exact expectation.
+    table = torch.from_numpy(load_golden("norm.npz")["u8_over_255"]).cuda()
+    want = table[imgs.long()] if normalize else imgs
     for engine in ("tensor", "bulk"):
         tiles = s.gather(pos, src_index=src, normalize=normalize, engine=engine)
         back = tiles.view(gh, gw, b, 3, P, P).permute(2, 3, 0, 4, 1, 5).reshape(b, 3, gh * P, gw * P)

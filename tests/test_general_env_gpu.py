@@ -173,6 +173,7 @@ def test_large_batch_properties_cfg3_shape():
     masks = env.bbox_masks
     total = masks.sum(dim=(1, 2))
     ar = torch.arange(b, device="cuda")
+    table = torch.from_numpy(load_golden("norm.npz")["u8_over_255"]).cuda()  # exact CPU `x / 255` per byte value
     visited_ref = torch.zeros_like(masks)
     visited_ref[ar, infos["positions"][:, 0], infos["positions"][:, 1]] = True
     stopped = torch.zeros(b, dtype=torch.bool, device="cuda")

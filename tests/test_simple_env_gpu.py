@@ -46,7 +46,7 @@ def test_collate_and_batched_entry_match_reference_fixtures():
 
     fx = load_golden("simple_env.npz")
     ref = scenario(fx, "collate")
-    members = fx["collate/members"].tolist()
+    members = ref.pop("members").tolist()
     # (a) per-env samples + collate_fn, exactly like the reference trainer
     samples = []
     for j, idx in enumerate(members):
@@ -122,6 +122,7 @@ def test_large_batch_properties_cfg2_shape():
     assert tuple(out["patches"].shape) == (b, T, 3, P, P) and out["patches"].dtype == torch.float32
     masks, pos = out["masks"].cpu(), out["positions"].cpu()
     delta = torch.tensor([(0, -1), (0, 1), (-1, 0), (1, 0), (-1, -1), (-1, 1), (1, -1), (1, 1), (0, 0)])
+    table = torch.from_numpy(load_golden("norm.npz")["u8_over_255"]).cuda()  # exact CPU `x / 255` per byte value
     assert bool(((masks == 0) | (masks == 1)).all()) and bool((masks[:, 0] == 1).all())
     assert bool((masks[:, 1:] <= masks[:, :-1]).all())  # recorded slots form a prefix
     cur = out["current_actions"].cpu()
@@ -130,7 +131,7 @@ def test_large_batch_properties_cfg2_shape():
         for t in range(T):
             if t < n:
                 y, x = pos[i, t].tolist()
-                want = images[i][:, y * P:(y + 1) * P, x * P:(x + 1) * P].float() / 255
+                want = table[images[i][:, y * P:(y + 1) * P, x * P:(x + 1) * P].long()]
                 assert torch.equal(out["patches"][i, t], want)
                 if t > 0:
                     assert torch.equal(pos[i, t], pos[i, t - 1] + delta[cur[i, t]])

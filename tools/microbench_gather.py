@@ -54,6 +54,11 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--engines", default="tensor,bulk")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--patches", default="")
+    ap.add_argument("--batches", default="")
+    ap.add_argument("--modes", default="f32,u8", help="f32 = fp32 copy, u8 = uint8 normalised")
+    ap.add_argument("--layouts", default="plain,focus")
+    ap.add_argument("--label", default="")
     args = ap.parse_args()
     peak = 6465.2
     try:
@@ -62,11 +67,17 @@ def main():
         pass
     combos = []
     patches = [448, 256] if args.quick else [128, 256, 448, 1024]
+    if args.patches:
+        patches = [int(v) for v in args.patches.split(",")]
     for P in patches:
-        batches = [b for b in ([64, 512, 2048, 8192] if not args.quick else [256, 2048]) if b * 3 * P * P * 4 <= 24 << 30]
+        batches = [64, 512, 2048, 8192] if not args.quick else [256, 2048]
+        if args.batches:
+            batches = [int(v) for v in args.batches.split(",")]
+        batches = [b for b in batches if b * 3 * P * P * 4 <= 24 << 30]
+        modes = [(torch.float32, False)] * ("f32" in args.modes) + [(torch.uint8, True)] * ("u8" in args.modes)
         for n in batches:
-            for dtype, normalize in ((torch.float32, False), (torch.uint8, True)):
-                for focus in (False, True):
+            for dtype, normalize in modes:
+                for focus in [False] * ("plain" in args.layouts) + [True] * ("focus" in args.layouts):
                     for engine in args.engines.split(","):
                         combos.append((P, n, dtype, normalize, focus, engine))
     lines = []
@@ -74,13 +85,15 @@ def main():
         try:
             r = bench_one(*c)
             r["frac_of_measured_peak"] = round(r["GBps"] / peak, 3)
+            if args.label:
+                r["label"] = args.label
         except Exception as e:  # keep sweeping
             r = {"P": c[0], "n": c[1], "engine": c[5], "error": repr(e)[:200]}
         print(json.dumps(r), flush=True)
         lines.append(r)
         torch.cuda.empty_cache()
     if args.out:
-        with open(args.out, "w") as f:
+        with open(args.out, "a") as f:
             for r in lines:
                 f.write(json.dumps(r) + "\n")
 
