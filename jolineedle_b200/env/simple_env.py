@@ -93,6 +93,20 @@ class NeedleSimpleEnv:
         self.visited_bbox_patches: Set[Position] = set()
         self._image_set: Optional[ImageSet] = None
 
+    def __deepcopy__(self, memo):
+        """``deepcopy(env)`` (supervised.py:295) copies the mutable episode state and shares the
+        immutable image and its device handle."""
+        import copy
+
+        clone = object.__new__(type(self))
+        memo[id(self)] = clone
+        for key, value in self.__dict__.items():
+            if key in ("image", "_image_set"):
+                setattr(clone, key, value)
+            else:
+                setattr(clone, key, copy.deepcopy(value, memo))
+        return clone
+
     # -- geometry (host integers) ------------------------------------------------------------
     def bbox_positions(self, raw_bbox: BBox, area_threshold: float = 0.05) -> Set[Position]:
         """Patches holding more than ``area_threshold`` of P^2 of the box, plus the patch of its
