@@ -147,28 +147,34 @@ int encode_slab_map(CUtensorMap* map, const void* ptr, int elem, int n_planes, i
 
 namespace {
 
-constexpr int kXformStages = 4, kXformWarps = 8;
+constexpr int kXformWarps = 8;
 
-// Pipeline shape of the gather kernels.  The defaults are the measured optimum on B200
-// (profiles/); JN_GATHER_TUNE="copy_stages,copy_ahead,copy_chunk_bytes,copy_ctas_per_sm,
-// xform_chunk_bytes,xform_ctas_per_sm" overrides them for tuning sweeps (0 keeps a default).
+// Pipeline shape of the gather kernels: stages of the shared-memory ring, load lookahead (copy
+// kernel), bytes per chunk and resident CTAs per SM.  The defaults come from sweeps on B200
+// (tools/tune_gather.py, profiles/); JN_GATHER_TUNE="copy_stages,copy_ahead,copy_chunk_bytes,
+// copy_ctas_per_sm,xform_stages,xform_chunk_bytes,xform_ctas_per_sm" overrides them (0 keeps a
+// default).
 struct GatherTune {
   int copy_stages = 6, copy_ahead = 3, copy_chunk = 32768, copy_ctas = 0;
-  int xform_chunk = 0, xform_ctas = 0;
+  int xform_stages = 4, xform_chunk = 0, xform_ctas = 0;
 };
 
-GatherTune gather_tune() {
+GatherTune gather_tune(int patch, int elem, bool plain_copy, bool focus, int engine) {
   GatherTune t;
+  (void)patch; (void)focus; (void)engine;
+  t.xform_chunk = elem == 4 ? 24576 : 16384;
   if (const char* env = getenv("JN_GATHER_TUNE")) {
-    int v[6] = {0, 0, 0, 0, 0, 0};
-    sscanf(env, "%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]);
+    int v[7] = {0, 0, 0, 0, 0, 0, 0};
+    sscanf(env, "%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6]);
     if (v[0] > 0) t.copy_stages = v[0];
     if (v[1] > 0) t.copy_ahead = v[1];
     if (v[2] > 0) t.copy_chunk = v[2];
     if (v[3] > 0) t.copy_ctas = v[3];
-    if (v[4] > 0) t.xform_chunk = v[4];
-    if (v[5] > 0) t.xform_ctas = v[5];
+    if (v[4] > 0) t.xform_stages = v[4];
+    if (v[5] > 0) t.xform_chunk = v[5];
+    if (v[6] > 0) t.xform_ctas = v[6];
   }
+  (void)plain_copy;
   return t;
 }
 
@@ -344,8 +350,8 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
   }
 
   // TMA engines: chunk geometry
-  const GatherTune tune = gather_tune();
-  const int target = plain_copy ? tune.copy_chunk : (tune.xform_chunk ? tune.xform_chunk : (set->elem == 4 ? 24576 : 16384));
+  const GatherTune tune = gather_tune(P, set->elem, plain_copy, focus, engine);
+  const int target = plain_copy ? tune.copy_chunk : tune.xform_chunk;
   const int rows = pick_rows(P, set->elem, target, focus);
   JN_REQUIRE(rows > 0, "patch row of %d bytes does not fit a shared-memory stage", P * set->elem);
   a.rows = rows; a.chunks_per_plane = P / rows;
@@ -369,23 +375,28 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
   if (tune.copy_stages == S && tune.copy_ahead == D)                                                               \
     return tensor ? launch_persistent(jnk::gather_copy_kernel<S, D, true>, a, map, 32, smem, dev, stream, tune.copy_ctas) \
                   : launch_persistent(jnk::gather_copy_kernel<S, D, false>, a, map, 32, smem, dev, stream, tune.copy_ctas);
-    JN_COPY(6, 3) JN_COPY(4, 2) JN_COPY(3, 2) JN_COPY(6, 4) JN_COPY(8, 4) JN_COPY(8, 6) JN_COPY(12, 6) JN_COPY(12, 9)
+    JN_COPY(6, 3) JN_COPY(2, 1) JN_COPY(3, 1) JN_COPY(3, 2) JN_COPY(4, 1) JN_COPY(4, 2) JN_COPY(4, 3) JN_COPY(6, 2)
+    JN_COPY(6, 4) JN_COPY(6, 5) JN_COPY(8, 4) JN_COPY(8, 6) JN_COPY(12, 6) JN_COPY(12, 9)
 #undef JN_COPY
     return fail(JN_ERR_INVALID, "JN_GATHER_TUNE: no copy kernel with %d stages / lookahead %d", tune.copy_stages,
                 tune.copy_ahead);
   }
-  const size_t smem = kXformStages * chunk_bytes + 2 * kXformStages * sizeof(uint64_t);
+  const size_t smem = tune.xform_stages * chunk_bytes + 2 * tune.xform_stages * sizeof(uint64_t);
   const int threads = (kXformWarps + 1) * 32;
   const bool tensor = engine == JN_ENGINE_TENSOR;
-#define JN_XFORM(mode)                                                                                           \
-  (tensor ? launch_persistent(jnk::gather_xform_kernel<mode, kXformStages, kXformWarps, true>, a, map, threads, smem, \
-                              dev, stream, tune.xform_ctas)                                                      \
-          : launch_persistent(jnk::gather_xform_kernel<mode, kXformStages, kXformWarps, false>, a, map, threads,  \
-                              smem, dev, stream, tune.xform_ctas))
-  if (normalize && !focus) return JN_XFORM(jnk::kNormPlain);
-  if (normalize && focus) return JN_XFORM(jnk::kNormFocus);
-  return JN_XFORM(jnk::kF32Focus);
+#define JN_XFORM_S(mode, S)                                                                                        \
+  if (tune.xform_stages == S)                                                                                      \
+    return tensor ? launch_persistent(jnk::gather_xform_kernel<mode, S, kXformWarps, true>, a, map, threads, smem, dev, \
+                                      stream, tune.xform_ctas)                                                     \
+                  : launch_persistent(jnk::gather_xform_kernel<mode, S, kXformWarps, false>, a, map, threads, smem, \
+                                      dev, stream, tune.xform_ctas);
+#define JN_XFORM(mode) JN_XFORM_S(mode, 4) JN_XFORM_S(mode, 2) JN_XFORM_S(mode, 3) JN_XFORM_S(mode, 6) JN_XFORM_S(mode, 8)
+  if (normalize && !focus) { JN_XFORM(jnk::kNormPlain) }
+  else if (normalize && focus) { JN_XFORM(jnk::kNormFocus) }
+  else { JN_XFORM(jnk::kF32Focus) }
 #undef JN_XFORM
+#undef JN_XFORM_S
+  return fail(JN_ERR_INVALID, "JN_GATHER_TUNE: no xform kernel with %d stages", tune.xform_stages);
 }
 
 // ------------------------------------------------------------------------------------------
