@@ -202,6 +202,38 @@ int jn_traj_expand(const int32_t* start_yx /*[n,2]*/, const int32_t* seg_begin /
                    int64_t* current_actions, int64_t* next_actions, int64_t* labels, float* masks,
                    int32_t* gather_src, int32_t* ep_len, int32_t* status, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Host-side planner of supervised episodes (no GPU involved; all pointers are HOST memory).
+ *
+ * The host half of NeedleSimpleEnv.generate_sample (simple_env.py:378-441,481-629,666-718):
+ * detection-patch pick, start position, greedy key-point order, random key points, detours and
+ * the STOP replacement moves -- with the reference's random streams reproduced bit for bit
+ * (numpy SeedSequence/PCG64/Generator, CPython random.choice on MT19937, CPython set iteration
+ * order).  Its output is the input of jn_traj_expand / jn_gather / jn_local_boxes.
+ *
+ *   boxes int64 [n, max_boxes, 4] (x1,y1,x2,y2), n_boxes int32 [n], rows / cols int32 [n];
+ *   seeds uint64 [n] + has_seed uint8 [n] (0 = draw OS entropy, like an unseeded numpy Generator);
+ *   start_yx int32 [n, 2] or NULL (= drawn: y then x);
+ *   mt_state uint32 [625]: the MT19937 words + index of python's global `random`
+ *   (random.getstate()[1]); updated in place so the caller can random.setstate() afterwards.
+ *
+ * JN_ERR_UNSUPPORTED for grids wider than 60 patches (numpy switches binomial algorithms there).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct jn_plan jn_plan;
+int jn_plan_create(jn_plan** out);
+void jn_plan_destroy(jn_plan* plan);
+const char* jn_plan_error(const jn_plan* plan);
+int jn_plan_run(jn_plan* plan, int n, const int64_t* boxes, const int32_t* n_boxes, int max_boxes,
+                const int32_t* rows, const int32_t* cols, int patch_size, const uint64_t* seeds,
+                const uint8_t* has_seed, int min_keypoints, int max_keypoints, int binomial,
+                const int32_t* start_yx, uint32_t* mt_state);
+int jn_plan_sizes(const jn_plan* plan, int* n_segments, int* n_draws, int* n_det);
+/* start [n,2], seg_begin [n+1], seg_to [S,2], seg_tgt [S,2], draw_begin [n+1], det_begin [n+1],
+ * det_yx [D,2] (int32); seg_flags [S], draws [Q] (uint8).  NULL pointers are skipped. */
+int jn_plan_export(const jn_plan* plan, int32_t* start, int32_t* seg_begin, int32_t* seg_to,
+                   int32_t* seg_tgt, int32_t* draw_begin, int32_t* det_begin, int32_t* det_yx,
+                   uint8_t* seg_flags, uint8_t* draws);
+
 #ifdef __cplusplus
 }
 #endif

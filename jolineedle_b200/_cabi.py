@@ -52,6 +52,12 @@ SIGNATURES = {
     "jn_returns_rows": (c_int, [_P, c_int64, _P, c_int64, c_int, c_int, _P, _P]),
     "jn_traj_expand": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, c_int, c_int, _P, _P, _P, _P, _P, _P,
                                _P, _P, _P]),
+    "jn_plan_create": (c_int, [POINTER(_P)]),
+    "jn_plan_destroy": (None, [_P]),
+    "jn_plan_error": (c_char_p, [_P]),
+    "jn_plan_run": (c_int, [_P, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P]),
+    "jn_plan_sizes": (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "jn_plan_export": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 
 # entry points that launch exactly one kernel of ours per successful call

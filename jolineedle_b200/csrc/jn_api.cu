@@ -161,8 +161,19 @@ struct GatherTune {
 
 GatherTune gather_tune(int patch, int elem, bool plain_copy, bool focus, int engine) {
   GatherTune t;
-  (void)patch; (void)focus; (void)engine;
-  t.xform_chunk = elem == 4 ? 24576 : 16384;
+  (void)engine; (void)plain_copy;
+  // Buckets by patch size (measured at P = 128 / 256 / 448 / 1024, both TMA engines; the entry is the
+  // setting whose *worse* engine was best -- profiles/r01/tune_sweep_summary.txt).  Shallow rings
+  // with several CTAs per SM beat one deep ring: 2-3 stages, lookahead 1, 2-4 CTAs/SM.
+  const int bucket = patch <= 128 ? 0 : patch <= 256 ? 1 : patch < 1024 ? 2 : 3;
+  static const int copy[4][4] = {{2, 1, 32768, 3}, {3, 1, 32768, 2}, {3, 1, 32768, 2}, {2, 1, 16384, 3}};
+  static const int norm_plain[4][3] = {{2, 16384, 3}, {3, 8192, 2}, {3, 16384, 1}, {2, 8192, 2}};
+  static const int norm_focus[4][3] = {{2, 16384, 4}, {3, 16384, 2}, {3, 16384, 2}, {2, 16384, 2}};
+  static const int f32_focus[4][3] = {{2, 16384, 3}, {3, 16384, 2}, {3, 16384, 2}, {3, 32768, 1}};
+  t.copy_stages = copy[bucket][0]; t.copy_ahead = copy[bucket][1]; t.copy_chunk = copy[bucket][2];
+  t.copy_ctas = copy[bucket][3];
+  const int(*x)[3] = elem == 4 ? f32_focus : (focus ? norm_focus : norm_plain);
+  t.xform_stages = x[bucket][0]; t.xform_chunk = x[bucket][1]; t.xform_ctas = x[bucket][2];
   if (const char* env = getenv("JN_GATHER_TUNE")) {
     int v[7] = {0, 0, 0, 0, 0, 0, 0};
     sscanf(env, "%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6]);

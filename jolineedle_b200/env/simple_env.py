@@ -345,157 +345,23 @@ class NeedleSimpleEnv:
         return out
 
 
+
 # ---------------------------------------------------------------------------------------------------
-# device half: plans -> tensors
+# device half (plans -> tensors) and the batched entry point live in trajectories.py
 # ---------------------------------------------------------------------------------------------------
-def expand_plans(
-    envs: Sequence[NeedleSimpleEnv],
-    plans: Sequence[EpisodePlan],
-    max_ep_len: int,
-    image_set: Optional[ImageSet] = None,
-    normalize: Optional[bool] = None,
-    engine: str = "auto",
-) -> Dict[str, torch.Tensor]:
-    """Turn host plans into the collated sample dict of the reference (keys ``patches``,
-    ``current_actions``, ``next_actions``, ``positions``, ``masks``, ``labels``,
-    ``local_bboxes``, ``patches_yolox``, ``bboxes_yolox``) with K0 + K3 + K1."""
-    lib = _cabi.lib()
-    n, T = len(envs), int(max_ep_len)
+def expand_plans(envs, plans, max_ep_len, image_set=None, normalize=None, engine="auto"):
+    """Turn host plans of these envs into the collated sample dict (see trajectories.py)."""
+    from .trajectories import expand_packed, pack_python_plans
+
     if image_set is None:
         image_set = ImageSet([e.image for e in envs], envs[0].patch_size)
     if normalize is None:
         normalize = envs[0]._normalize
-    dev, P = image_set.device, image_set.patch_size
-    n_max = max(len(e.raw_bboxes) for e in envs)
-
-    # ---- pack the plans (host) ----
-    seg_begin = np.zeros(n + 1, dtype=np.int32)
-    draw_begin = np.zeros(n + 1, dtype=np.int32)
-    det_begin = np.zeros(n + 1, dtype=np.int32)
-    for i, pl in enumerate(plans):
-        seg_begin[i + 1] = seg_begin[i] + len(pl.seg_to)
-        draw_begin[i + 1] = draw_begin[i] + len(pl.draws)
-        det_begin[i + 1] = det_begin[i] + len(pl.det_positions)
-    n_seg, n_draw, n_det = int(seg_begin[-1]), int(draw_begin[-1]), int(det_begin[-1])
-    start = np.array([pl.start for pl in plans], dtype=np.int32).reshape(n, 2)
-    seg_to = np.array([c for pl in plans for c in pl.seg_to], dtype=np.int32).reshape(n_seg, 2)
-    seg_tgt = np.array([c for pl in plans for c in pl.seg_tgt], dtype=np.int32).reshape(n_seg, 2)
-    rows = np.array([e.patch_height for e in envs], dtype=np.int32)
-    cols = np.array([e.patch_width for e in envs], dtype=np.int32)
-    n_boxes = np.array([len(e.raw_bboxes) for e in envs], dtype=np.int32)
-    det_src = np.repeat(np.arange(n, dtype=np.int32), np.diff(det_begin))
-    i32 = np.concatenate([start.ravel(), seg_begin, seg_to.ravel(), seg_tgt.ravel(), draw_begin, rows, cols, n_boxes,
-                          det_src])
-    u8 = np.concatenate([np.array([f for pl in plans for f in pl.seg_first], dtype=np.uint8),
-                         np.array([d for pl in plans for d in pl.draws], dtype=np.uint8),
-                         np.zeros(1, dtype=np.uint8)])
-    boxes = np.zeros((n, max(n_max, 1), 4), dtype=np.int64)
-    for i, e in enumerate(envs):
-        for k, b in enumerate(e.raw_bboxes):
-            boxes[i, k] = (int(b.up_left.x), int(b.up_left.y), int(b.bottom_right.x), int(b.bottom_right.y))
-    det_pos = np.array([c for pl in plans for c in pl.det_positions], dtype=np.int64).reshape(n_det, 2)
-    i64 = np.concatenate([boxes.ravel(), det_pos.ravel()])
-
-    d_i32 = torch.from_numpy(i32).to(dev, non_blocking=True)
-    d_u8 = torch.from_numpy(u8).to(dev, non_blocking=True)
-    d_i64 = torch.from_numpy(i64).to(dev, non_blocking=True)
-
-    def take(buf, offset, count):
-        return buf[offset : offset + count], offset + count
-
-    o = 0
-    d_start, o = take(d_i32, o, 2 * n)
-    d_seg_begin, o = take(d_i32, o, n + 1)
-    d_seg_to, o = take(d_i32, o, 2 * n_seg)
-    d_seg_tgt, o = take(d_i32, o, 2 * n_seg)
-    d_draw_begin, o = take(d_i32, o, n + 1)
-    d_rows, o = take(d_i32, o, n)
-    d_cols, o = take(d_i32, o, n)
-    d_nboxes, o = take(d_i32, o, n)
-    d_det_src, o = take(d_i32, o, n_det)
-    d_flags, d_draws = d_u8[:n_seg], d_u8[n_seg : n_seg + n_draw + 1]
-    d_boxes = d_i64[: boxes.size].view(n, max(n_max, 1), 4)
-    d_det_pos = d_i64[boxes.size :].view(n_det, 2)
-
-    words = int(max((r * c + 31) // 32 for r, c in zip(rows.tolist(), cols.tolist())))
-    stream = _cabi.stream_ptr(dev)
-    status = torch.zeros(1, dtype=torch.int32, device=dev)
-    area = torch.empty((n, words), dtype=torch.int32, device=dev)
-    out = {
-        "patches": torch.empty((n, T) + image_set.out_shape(1, False)[1:], dtype=torch.float32, device=dev),
-        "current_actions": torch.empty((n, T), dtype=torch.long, device=dev),
-        "next_actions": torch.empty((n, T), dtype=torch.long, device=dev),
-        "positions": torch.empty((n, T, 2), dtype=torch.long, device=dev),
-        "masks": torch.empty((n, T), dtype=torch.float32, device=dev),
-        "labels": torch.empty((n, T), dtype=torch.long, device=dev),
-        "local_bboxes": torch.empty((n, T, n_max, 6), dtype=torch.float32, device=dev),
-    }
-    if image_set.out_dtype(normalize) != torch.float32:
-        raise ValueError("supervised samples are float32: pass float32 images, or uint8 images with normalize=True")
-    gather_src = torch.empty((n, T), dtype=torch.int32, device=dev)
-    ep_len = torch.empty((n,), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
-        # K0: 5 %-area bitmaps (labels = inside_bbox, simple_env.py:225,478)
-        _cabi.check(lib.jn_patch_bitmaps(d_boxes.data_ptr(), d_nboxes.data_ptr(), n, max(n_max, 1), P, 0, 0,
-                                         d_rows.data_ptr(), d_cols.data_ptr(), _cabi.RULE_AREA5, area.data_ptr(),
-                                         words, stream))
-        # K3: plan -> per-step records
-        _cabi.check(lib.jn_traj_expand(
-            d_start.data_ptr(), d_seg_begin.data_ptr(), d_seg_to.data_ptr(), d_seg_tgt.data_ptr(),
-            d_flags.data_ptr(), d_draw_begin.data_ptr(), d_draws.data_ptr(), area.data_ptr(), words,
-            d_cols.data_ptr(), n, T, out["positions"].data_ptr(), out["current_actions"].data_ptr(),
-            out["next_actions"].data_ptr(), out["labels"].data_ptr(), out["masks"].data_ptr(),
-            gather_src.data_ptr(), ep_len.data_ptr(), status.data_ptr(), stream))
-        # per-step local boxes (simple_env.py:479)
-        if n_max > 0:
-            _cabi.check(lib.jn_local_boxes(d_boxes.data_ptr(), d_nboxes.data_ptr(), n_max, P,
-                                           out["positions"].data_ptr(), gather_src.data_ptr(), n * T,
-                                           out["local_bboxes"].data_ptr(), stream))
-    # K1: the glimpses themselves, straight into [B, T, C, P, P]; padded slots are zero-filled
-    image_set.gather(out["positions"].view(n * T, 2), src_index=gather_src.view(n * T),
-                     out=out["patches"].view((n * T,) + out["patches"].shape[2:]), normalize=normalize,
-                     engine=engine, status=status, tag="trajectory")
-    # detection patches: every box patch + one random empty patch per image (simple_env.py:397-441)
-    out["patches_yolox"] = image_set.gather(d_det_pos, src_index=d_det_src, normalize=normalize, engine=engine,
-                                            status=status, tag="detection")
-    det_boxes = torch.empty((n_det, n_max, 6), dtype=torch.float32, device=dev)
-    if n_max > 0 and n_det > 0:
-        with torch.cuda.device(dev):
-            _cabi.check(lib.jn_local_boxes(d_boxes.data_ptr(), d_nboxes.data_ptr(), n_max, P, d_det_pos.data_ptr(),
-                                           d_det_src.data_ptr(), n_det, det_boxes.data_ptr(), stream))
-    out["bboxes_yolox"] = det_boxes
-    out["_ep_len"] = ep_len
-    out["_status"] = status
-    return out
+    return expand_packed(image_set, pack_python_plans(envs, plans), max_ep_len, normalize, engine)
 
 
-def generate_trajectories(
-    batch: Dict,
-    patch_size: int,
-    max_seq_len: int,
-    min_keypoints: int,
-    max_keypoints: int,
-    binomial_keypoints: bool = False,
-    position: Optional[Position] = None,
-    seeds: Optional[Sequence[Optional[int]]] = None,
-    normalize: bool = False,
-    device=None,
-    engine: str = "auto",
-) -> Dict[str, torch.Tensor]:
-    """Batched supervised trajectories (``SupervisedTrainer.generate_trajectories``,
-    supervised.py:95-136): ``batch`` holds lists ``image`` ([C,H,W] tensors), ``bboxes`` (lists
-    of ``BBox``) and ``class_id``.  Returns the collated dict of the reference on the GPU.
-    ``seeds`` (one per image) makes the plans reproducible; the reference builds unseeded envs."""
-    images = batch["image"]
-    envs = [
-        NeedleSimpleEnv(images[i], patch_size, batch["bboxes"][i], None if seeds is None else seeds[i],
-                        normalize=normalize, device=device)
-        for i in range(len(images))
-    ]
-    plans = [e.plan_sample(min_keypoints, max_keypoints, binomial_keypoints, position) for e in envs]
-    out = expand_plans(envs, plans, max_seq_len, normalize=normalize, engine=engine)
-    dev = out["patches"].device
-    out["class_id"] = torch.tensor([int(c) for c in batch["class_id"]], dtype=torch.long, device=dev)
-    out.pop("_ep_len")
-    out.pop("_status")
-    return out
+def generate_trajectories(*args, **kwargs):
+    """Batched supervised trajectories (supervised.py:95-136); see trajectories.py."""
+    from .trajectories import generate_trajectories as impl
+
+    return impl(*args, **kwargs)

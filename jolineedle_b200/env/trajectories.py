@@ -1,0 +1,316 @@
+"""Batched supervised trajectories: host plans -> device tensors (reference:
+``SupervisedTrainer.generate_trajectories``, ``src/supervised.py:95-136``).
+
+Two planners produce the same :class:`PackedPlans`:
+
+  ``native``  ``jn_plan_run`` (csrc/jn_planner.cpp): the reference's random streams (numpy
+              PCG64 / python MT19937 / CPython set order) restated in C++; ~1 us per episode.
+  ``python``  ``NeedleSimpleEnv.plan_sample``: calls the real numpy / random / set objects;
+              used for inputs the native planner does not cover (float boxes, grids wider than
+              60 patches, seeds above 2^64) and as its cross-check in the tests.
+
+The device half (:func:`expand_packed`) is shared: K0 5 %-area bitmaps, K3 ``jn_traj_expand``,
+``jn_local_boxes`` and the K1 gathers, all on torch's current stream.
+"""
+import ctypes
+import random
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import _cabi
+from ..gather import ImageSet
+from ..utils import Position
+
+
+class PackedPlans:
+    """Flat host arrays describing ``n`` planned episodes (see ``jn_traj_expand``)."""
+
+    __slots__ = ("n", "start", "seg_begin", "seg_to", "seg_tgt", "seg_flags", "draw_begin", "draws", "det_begin",
+                 "det_yx", "rows", "cols", "n_boxes", "boxes", "n_max")
+
+
+# ---------------------------------------------------------------------------------------------------
+# python planner -> packed
+# ---------------------------------------------------------------------------------------------------
+def boxes_array(bboxes: Sequence[Sequence], n_max: Optional[int] = None):
+    """``[n, max(n_max, 1), 4]`` int64 x1,y1,x2,y2 + per-image counts; ``exact`` tells whether every
+    coordinate was an integer (the native planner and the kernels work on integer pixels)."""
+    n = len(bboxes)
+    counts = np.array([len(b) for b in bboxes], dtype=np.int32)
+    n_max = int(counts.max()) if n_max is None and n else (n_max or 0)
+    arr = np.zeros((n, max(n_max, 1), 4), dtype=np.int64)
+    total = int(counts.sum())
+    if total == 0:
+        return arr, counts, n_max, True
+    # one conversion for the whole batch: BBox = ((y1, x1), (y2, x2)) -> [total, 2, 2]
+    flat = np.asarray([b for boxes in bboxes for b in boxes])
+    exact = bool(np.issubdtype(flat.dtype, np.integer)) or bool(np.all(flat == np.floor(flat)))
+    flat = flat.reshape(total, 4)[:, [1, 0, 3, 2]].astype(np.int64)  # -> x1, y1, x2, y2 (truncation like `.int()`)
+    image = np.repeat(np.arange(n), counts)
+    slot = np.arange(total) - np.repeat(np.cumsum(counts) - counts, counts)
+    arr[image, slot] = flat
+    return arr, counts, n_max, exact
+
+
+def pack_python_plans(envs, plans) -> PackedPlans:
+    n = len(envs)
+    p = PackedPlans()
+    p.n = n
+    p.seg_begin = np.zeros(n + 1, dtype=np.int32)
+    p.draw_begin = np.zeros(n + 1, dtype=np.int32)
+    p.det_begin = np.zeros(n + 1, dtype=np.int32)
+    for i, pl in enumerate(plans):
+        p.seg_begin[i + 1] = p.seg_begin[i] + len(pl.seg_to)
+        p.draw_begin[i + 1] = p.draw_begin[i] + len(pl.draws)
+        p.det_begin[i + 1] = p.det_begin[i] + len(pl.det_positions)
+    n_seg, n_det = int(p.seg_begin[-1]), int(p.det_begin[-1])
+    p.start = np.array([pl.start for pl in plans], dtype=np.int32).reshape(n, 2)
+    p.seg_to = np.array([c for pl in plans for c in pl.seg_to], dtype=np.int32).reshape(n_seg, 2)
+    p.seg_tgt = np.array([c for pl in plans for c in pl.seg_tgt], dtype=np.int32).reshape(n_seg, 2)
+    p.seg_flags = np.array([f for pl in plans for f in pl.seg_first], dtype=np.uint8)
+    p.draws = np.array([d for pl in plans for d in pl.draws], dtype=np.uint8)
+    p.det_yx = np.array([c for pl in plans for c in pl.det_positions], dtype=np.int32).reshape(n_det, 2)
+    p.rows = np.array([e.patch_height for e in envs], dtype=np.int32)
+    p.cols = np.array([e.patch_width for e in envs], dtype=np.int32)
+    p.boxes, p.n_boxes, p.n_max, _ = boxes_array([e.raw_bboxes for e in envs])
+    return p
+
+
+# ---------------------------------------------------------------------------------------------------
+# native planner -> packed
+# ---------------------------------------------------------------------------------------------------
+class _NativePlan:
+    def __init__(self):
+        self.handle = ctypes.c_void_p()
+        _cabi.check(_cabi.lib().jn_plan_create(ctypes.byref(self.handle)))
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                _cabi.lib().jn_plan_destroy(h)
+            except Exception:
+                pass
+
+
+_native_plan: Optional[_NativePlan] = None
+
+
+def native_supported(rows: np.ndarray, cols: np.ndarray, exact_boxes: bool, seeds) -> bool:
+    if not exact_boxes or (len(rows) and (int(rows.max()) > 60 or int(cols.max()) > 60)):
+        return False
+    if seeds is not None:
+        for s in seeds:
+            if s is not None and not (isinstance(s, (int, np.integer)) and 0 <= int(s) < (1 << 64)):
+                return False
+    return True
+
+
+def plan_native(boxes: np.ndarray, n_boxes: np.ndarray, n_max: int, rows: np.ndarray, cols: np.ndarray,
+                patch_size: int, seeds: Optional[Sequence[Optional[int]]], min_keypoints: int, max_keypoints: int,
+                binomial_keypoints: bool, position: Optional[Position]) -> PackedPlans:
+    """Run ``jn_plan_run`` on the host.  Python's global ``random`` state is handed to the C++
+    side and written back, so interleaving with other users of ``random`` behaves as if
+    ``random.choice`` had been called from python."""
+    global _native_plan
+    if _native_plan is None:
+        _native_plan = _NativePlan()
+    lib, h = _cabi.lib(), _native_plan.handle
+    n = len(rows)
+    seed_arr = np.zeros(n, dtype=np.uint64)
+    has_seed = np.zeros(n, dtype=np.uint8)
+    if seeds is not None:
+        for i, s in enumerate(seeds):
+            if s is not None:
+                seed_arr[i], has_seed[i] = int(s), 1
+    start = None
+    if position is not None:
+        start = np.tile(np.array([int(position[0]), int(position[1])], dtype=np.int32), (n, 1))
+    version, mt_words, gauss = random.getstate()
+    mt = np.array(mt_words, dtype=np.uint32)
+    rc = lib.jn_plan_run(h, n, boxes.ctypes.data, n_boxes.ctypes.data, boxes.shape[1] if n_max > 0 else 0,
+                         rows.ctypes.data, cols.ctypes.data, patch_size, seed_arr.ctypes.data, has_seed.ctypes.data,
+                         min_keypoints, max_keypoints, 1 if binomial_keypoints else 0,
+                         None if start is None else start.ctypes.data, mt.ctypes.data)
+    if rc != _cabi.JN_OK:
+        msg = lib.jn_plan_error(h).decode("utf-8", "replace")
+        if rc == _cabi.JN_ERR_INVALID:
+            raise AssertionError(msg)  # e.g. start position outside the grid (simple_env.py:73-74)
+        raise _cabi.NativeLibraryError(f"native planner failed (status {rc}): {msg}")
+    random.setstate((version, tuple(mt.tolist()), gauss))
+    n_seg, n_draw, n_det = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    lib.jn_plan_sizes(h, ctypes.byref(n_seg), ctypes.byref(n_draw), ctypes.byref(n_det))
+    p = PackedPlans()
+    p.n = n
+    p.start = np.empty((n, 2), dtype=np.int32)
+    p.seg_begin = np.empty(n + 1, dtype=np.int32)
+    p.seg_to = np.empty((n_seg.value, 2), dtype=np.int32)
+    p.seg_tgt = np.empty((n_seg.value, 2), dtype=np.int32)
+    p.draw_begin = np.empty(n + 1, dtype=np.int32)
+    p.det_begin = np.empty(n + 1, dtype=np.int32)
+    p.det_yx = np.empty((n_det.value, 2), dtype=np.int32)
+    p.seg_flags = np.empty(n_seg.value, dtype=np.uint8)
+    p.draws = np.empty(n_draw.value, dtype=np.uint8)
+    lib.jn_plan_export(h, p.start.ctypes.data, p.seg_begin.ctypes.data, p.seg_to.ctypes.data, p.seg_tgt.ctypes.data,
+                       p.draw_begin.ctypes.data, p.det_begin.ctypes.data, p.det_yx.ctypes.data,
+                       p.seg_flags.ctypes.data, p.draws.ctypes.data)
+    p.rows, p.cols, p.n_boxes, p.boxes, p.n_max = rows, cols, n_boxes, boxes, n_max
+    return p
+
+
+# ---------------------------------------------------------------------------------------------------
+# device half
+# ---------------------------------------------------------------------------------------------------
+def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normalize: bool = False,
+                  engine: str = "auto") -> Dict[str, torch.Tensor]:
+    """Packed plans -> the collated sample dict of the reference (keys ``patches``,
+    ``current_actions``, ``next_actions``, ``positions``, ``masks``, ``labels``, ``local_bboxes``,
+    ``patches_yolox``, ``bboxes_yolox``; plus ``_ep_len`` / ``_status`` for diagnostics)."""
+    lib = _cabi.lib()
+    n, T, n_max = p.n, int(max_ep_len), p.n_max
+    dev, P = image_set.device, image_set.patch_size
+    if image_set.out_dtype(normalize) != torch.float32:
+        raise ValueError("supervised samples are float32: pass float32 images, or uint8 images with normalize=True")
+    n_seg, n_draw, n_det = len(p.seg_flags), len(p.draws), len(p.det_yx)
+    det_src = np.repeat(np.arange(n, dtype=np.int32), np.diff(p.det_begin))
+    # three uploads: int32 block, uint8 block, int64 block
+    i32 = np.concatenate([p.start.ravel(), p.seg_begin, p.seg_to.ravel(), p.seg_tgt.ravel(), p.draw_begin, p.rows,
+                          p.cols, p.n_boxes, det_src])
+    u8 = np.concatenate([p.seg_flags, p.draws, np.zeros(1, dtype=np.uint8)])
+    i64 = np.concatenate([p.boxes.ravel(), p.det_yx.astype(np.int64).ravel()])
+    d_i32 = torch.from_numpy(i32).to(dev, non_blocking=True)
+    d_u8 = torch.from_numpy(u8).to(dev, non_blocking=True)
+    d_i64 = torch.from_numpy(i64).to(dev, non_blocking=True)
+
+    o = 0
+
+    def take(count):
+        nonlocal o
+        view = d_i32[o:o + count]
+        o += count
+        return view
+
+    d_start, d_seg_begin = take(2 * n), take(n + 1)
+    d_seg_to, d_seg_tgt = take(2 * n_seg), take(2 * n_seg)
+    d_draw_begin, d_rows, d_cols, d_nboxes, d_det_src = take(n + 1), take(n), take(n), take(n), take(n_det)
+    d_flags, d_draws = d_u8[:n_seg], d_u8[n_seg:n_seg + n_draw + 1]
+    d_boxes = d_i64[:p.boxes.size].view(p.boxes.shape)
+    d_det_pos = d_i64[p.boxes.size:].view(n_det, 2)
+
+    words = int(((p.rows.astype(np.int64) * p.cols + 31) // 32).max())
+    stream = _cabi.stream_ptr(dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    area = torch.empty((n, words), dtype=torch.int32, device=dev)
+    out = {
+        "patches": torch.empty((n, T) + image_set.out_shape(1, False)[1:], dtype=torch.float32, device=dev),
+        "current_actions": torch.empty((n, T), dtype=torch.long, device=dev),
+        "next_actions": torch.empty((n, T), dtype=torch.long, device=dev),
+        "positions": torch.empty((n, T, 2), dtype=torch.long, device=dev),
+        "masks": torch.empty((n, T), dtype=torch.float32, device=dev),
+        "labels": torch.empty((n, T), dtype=torch.long, device=dev),
+        "local_bboxes": torch.empty((n, T, n_max, 6), dtype=torch.float32, device=dev),
+    }
+    gather_src = torch.empty((n, T), dtype=torch.int32, device=dev)
+    ep_len = torch.empty((n,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        # K0: 5 %-area bitmaps (labels = inside_bbox, simple_env.py:225,478)
+        _cabi.check(lib.jn_patch_bitmaps(d_boxes.data_ptr(), d_nboxes.data_ptr(), n, p.boxes.shape[1], P, 0, 0,
+                                         d_rows.data_ptr(), d_cols.data_ptr(), _cabi.RULE_AREA5, area.data_ptr(),
+                                         words, stream))
+        # K3: plan -> per-step records
+        _cabi.check(lib.jn_traj_expand(
+            d_start.data_ptr(), d_seg_begin.data_ptr(), d_seg_to.data_ptr(), d_seg_tgt.data_ptr(),
+            d_flags.data_ptr(), d_draw_begin.data_ptr(), d_draws.data_ptr(), area.data_ptr(), words,
+            d_cols.data_ptr(), n, T, out["positions"].data_ptr(), out["current_actions"].data_ptr(),
+            out["next_actions"].data_ptr(), out["labels"].data_ptr(), out["masks"].data_ptr(),
+            gather_src.data_ptr(), ep_len.data_ptr(), status.data_ptr(), stream))
+        # per-step local boxes (simple_env.py:479)
+        if n_max > 0:
+            _cabi.check(lib.jn_local_boxes(d_boxes.data_ptr(), d_nboxes.data_ptr(), n_max, P,
+                                           out["positions"].data_ptr(), gather_src.data_ptr(), n * T,
+                                           out["local_bboxes"].data_ptr(), stream))
+    # K1: the glimpses themselves, straight into [B, T, C, P, P]; padded slots are zero-filled
+    image_set.gather(out["positions"].view(n * T, 2), src_index=gather_src.view(n * T),
+                     out=out["patches"].view((n * T,) + out["patches"].shape[2:]), normalize=normalize,
+                     engine=engine, status=status, tag="trajectory")
+    # detection patches: every box patch + one random empty patch per image (simple_env.py:397-441)
+    out["patches_yolox"] = image_set.gather(d_det_pos, src_index=d_det_src, normalize=normalize, engine=engine,
+                                            status=status, tag="detection")
+    det_boxes = torch.empty((n_det, n_max, 6), dtype=torch.float32, device=dev)
+    if n_max > 0 and n_det > 0:
+        with torch.cuda.device(dev):
+            _cabi.check(lib.jn_local_boxes(d_boxes.data_ptr(), d_nboxes.data_ptr(), n_max, P, d_det_pos.data_ptr(),
+                                           d_det_src.data_ptr(), n_det, det_boxes.data_ptr(), stream))
+    out["bboxes_yolox"] = det_boxes
+    out["_ep_len"] = ep_len
+    out["_status"] = status
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# batched entry point
+# ---------------------------------------------------------------------------------------------------
+def plan_batch(bboxes: Sequence[Sequence], heights: Sequence[int], widths: Sequence[int], patch_size: int,
+               min_keypoints: int, max_keypoints: int, binomial_keypoints: bool = False,
+               position: Optional[Position] = None, seeds: Optional[Sequence[Optional[int]]] = None,
+               planner: str = "auto") -> PackedPlans:
+    """Host half for a batch of images given only their sizes and boxes (no pixel is touched)."""
+    for h, w in zip(heights, widths):
+        # same precondition as get_patch (simple_env.py:68-69)
+        assert h % patch_size == 0 and w % patch_size == 0, f"image {h}x{w} is not a multiple of {patch_size}"
+    rows = np.array([h // patch_size for h in heights], dtype=np.int32)
+    cols = np.array([w // patch_size for w in widths], dtype=np.int32)
+    boxes, n_boxes, n_max, exact = boxes_array(bboxes)
+    if planner not in ("auto", "native", "python"):
+        raise ValueError(f"unknown planner {planner!r}")
+    use_native = planner != "python" and native_supported(rows, cols, exact, seeds)
+    if planner == "native" and not use_native:
+        raise ValueError("the native planner needs integer boxes, grids up to 60x60 and seeds below 2**64")
+    if use_native:
+        return plan_native(boxes, n_boxes, n_max, rows, cols, patch_size, seeds, min_keypoints, max_keypoints,
+                           binomial_keypoints, position)
+    from .simple_env import NeedleSimpleEnv
+
+    class _Shape:  # plan_sample only needs the image's shape
+        def __init__(self, h, w):
+            self.shape = (3, h, w)
+            self.is_cuda = True
+
+    envs = [NeedleSimpleEnv(_Shape(heights[i], widths[i]), patch_size, bboxes[i], None if seeds is None else seeds[i])
+            for i in range(len(bboxes))]
+    plans = [e.plan_sample(min_keypoints, max_keypoints, binomial_keypoints, position) for e in envs]
+    return pack_python_plans(envs, plans)
+
+
+def generate_trajectories(
+    batch: Dict,
+    patch_size: int,
+    max_seq_len: int,
+    min_keypoints: int,
+    max_keypoints: int,
+    binomial_keypoints: bool = False,
+    position: Optional[Position] = None,
+    seeds: Optional[Sequence[Optional[int]]] = None,
+    normalize: bool = False,
+    device=None,
+    engine: str = "auto",
+    planner: str = "auto",
+) -> Dict[str, torch.Tensor]:
+    """Batched supervised trajectories (``SupervisedTrainer.generate_trajectories``,
+    supervised.py:95-136): ``batch`` holds lists ``image`` ([C,H,W] tensors), ``bboxes`` (lists
+    of ``BBox``) and ``class_id``.  Returns the collated dict of the reference on the GPU.
+    ``seeds`` (one per image) makes the plans reproducible; the reference builds unseeded envs.
+    CPU images are uploaded to ``device`` first (there is no CPU path)."""
+    images: List[torch.Tensor] = list(batch["image"])
+    if device is not None:
+        images = [im if im.is_cuda else im.to(device, non_blocking=True) for im in images]
+    packed = plan_batch(batch["bboxes"], [im.shape[1] for im in images], [im.shape[2] for im in images], patch_size,
+                        min_keypoints, max_keypoints, binomial_keypoints, position, seeds, planner)
+    image_set = ImageSet(images, patch_size)
+    out = expand_packed(image_set, packed, max_seq_len, normalize, engine)
+    out["class_id"] = torch.tensor([int(c) for c in batch["class_id"]], dtype=torch.long, device=image_set.device)
+    out.pop("_ep_len")
+    out.pop("_status")
+    return out

@@ -198,7 +198,7 @@ def test_large_batch_properties_cfg3_shape():
             k = torch.randint(0, b, (16,), generator=torch.Generator().manual_seed(t)).tolist()
             for i in k:
                 y, x = pos[i].tolist()
-                want = images[i, :, y * P:(y + 1) * P, x * P:(x + 1) * P].float() / 255
+                want = table[images[i, :, y * P:(y + 1) * P, x * P:(x + 1) * P].long()]
                 assert torch.equal(patches[i, 0], want)
     assert torch.equal(env.visited_patches, visited_ref)
     env.check_status()

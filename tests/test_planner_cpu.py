@@ -72,3 +72,112 @@ def test_value_types():
     t = bboxes_to_tensor(b)
     assert t.tolist() == [[1, 2, 5, 8], [0, 0, 3, 3]]  # x1, y1, x2, y2
     assert pixel_pos_to_patch_pos(Position(447, 448), 448) == Position(0, 1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# native (C++) planner == python planner (real numpy / random / set), no GPU needed
+# ---------------------------------------------------------------------------------------------------
+def _random_case(rng, n):
+    P = int(rng.choice([16, 32, 64, 448]))
+    heights, widths, bboxes = [], [], []
+    for _ in range(n):
+        gh, gw = int(rng.integers(1, 12)), int(rng.integers(1, 12))
+        h, w = gh * P, gw * P
+        boxes = []
+        for _ in range(int(rng.integers(0, 5))):
+            bw, bh = (int(v) for v in rng.integers(1, 3 * P, size=2))
+            x1 = int(rng.integers(-P // 2, w))  # may start left of / above the image or end outside of it
+            y1 = int(rng.integers(-P // 2, h))
+            boxes.append(BBox(Position(y1, x1), Position(y1 + bh, x1 + bw)))
+        heights.append(h); widths.append(w); bboxes.append(boxes)
+    return P, heights, widths, bboxes
+
+
+def _assert_same_plans(a, b):
+    for f in ("start", "seg_begin", "seg_to", "seg_tgt", "seg_flags", "draw_begin", "draws", "det_begin", "det_yx",
+              "rows", "cols", "n_boxes"):
+        x, y = getattr(a, f), getattr(b, f)
+        assert x.dtype == y.dtype and np.array_equal(x, y), f
+    assert np.array_equal(a.boxes[:, :max(a.n_max, 1)], b.boxes[:, :max(b.n_max, 1)]) and a.n_max == b.n_max
+
+
+def test_native_planner_reproduces_the_python_planner():
+    import random
+
+    from jolineedle_b200.env.trajectories import plan_batch
+
+    rng = np.random.default_rng(2024)
+    n_episodes = 0
+    for it in range(120):
+        n = int(rng.integers(1, 24))
+        P, heights, widths, bboxes = _random_case(rng, n)
+        binomial = bool(rng.integers(0, 2))
+        kmin = int(rng.integers(0, 3)); kmax = kmin + int(rng.integers(0, 4))
+        seeds = [int(s) for s in rng.integers(0, 2**63, size=n)]
+        if it % 5 == 0:
+            seeds[0] = 0
+            seeds[-1] = 2**64 - 1
+        position = None
+        if it % 3 == 0:
+            position = Position(int(rng.integers(0, min(heights) // P)), int(rng.integers(0, min(widths) // P)))
+        random.seed(it)
+        py = plan_batch(bboxes, heights, widths, P, kmin, kmax, binomial, position, seeds, planner="python")
+        state_py = random.getstate()
+        random.seed(it)
+        nat = plan_batch(bboxes, heights, widths, P, kmin, kmax, binomial, position, seeds, planner="native")
+        assert random.getstate() == state_py, "python's global random stream must advance identically"
+        _assert_same_plans(py, nat)
+        n_episodes += n
+    assert n_episodes > 1000
+
+
+def test_native_planner_reproduces_reference_fixtures():
+    """Golden trajectories of the unmodified reference, through native plan + sequential expansion."""
+    import random
+    from types import SimpleNamespace
+
+    from jolineedle_b200.env.trajectories import plan_batch
+
+    fx = load_golden("simple_env.npz")
+    for name in fx["names"]:
+        c, cfg = simple_case(fx, str(name))
+        seed_python_random(cfg["seed"])
+        boxes = [BBox(Position(y1, x1), Position(y2, x2)) for (x1, y1, x2, y2) in c["raw_boxes"].tolist()]
+        pos = None if cfg["position"] is None else Position(*cfg["position"])
+        _, h, w = c["u8"].shape
+        p = plan_batch([boxes], [h], [w], cfg["P"], cfg["kmin"], cfg["kmax"], cfg["binomial"], pos, [cfg["seed"]],
+                       planner="native")
+        plan = SimpleNamespace(start=tuple(p.start[0].tolist()), seg_to=[tuple(v) for v in p.seg_to.tolist()],
+                               seg_tgt=[tuple(v) for v in p.seg_tgt.tolist()], seg_first=p.seg_flags.tolist(),
+                               draws=p.draws.tolist())
+        inside = {tuple(r) for r in c["bbox_patches"].tolist()}
+        got = expand_plan_host(plan, cfg["T"], lambda y, x: (y, x) in inside)
+        for k in ("positions", "current_actions", "next_actions", "labels", "masks"):
+            assert np.array_equal(got[k], c[k]), (name, k)
+        P = cfg["P"]
+        img = to_f32(c["u8"])
+        tiles = torch.stack([img[:, y * P:(y + 1) * P, x * P:(x + 1) * P] for (y, x) in p.det_yx.tolist()])
+        assert np.array_equal(tiles.numpy(), c["patches_yolox"]), name
+
+
+def test_native_planner_unseeded_and_unsupported_inputs():
+    from jolineedle_b200.env.trajectories import plan_batch
+
+    boxes = [[BBox(Position(10, 10), Position(60, 90))]]
+    a = plan_batch(boxes, [128], [160], 32, 0, 3, True, None, None, planner="native")  # OS entropy: just runs
+    assert a.n == 1 and a.seg_begin[-1] >= 1
+    # float boxes -> python planner; forcing native is an error
+    fboxes = [[BBox(Position(10.5, 10.25), Position(60.0, 90.0))]]
+    b = plan_batch(fboxes, [128], [160], 32, 0, 0, False, Position(0, 0), [3], planner="auto")
+    assert b.n == 1
+    try:
+        plan_batch(fboxes, [128], [160], 32, 0, 0, False, None, [3], planner="native")
+        raise RuntimeError("expected ValueError")
+    except ValueError:
+        pass
+    # start position outside the grid -> AssertionError like get_patch (simple_env.py:73-74)
+    try:
+        plan_batch(boxes, [128], [160], 32, 0, 0, False, Position(9, 0), [1], planner="native")
+        raise RuntimeError("expected AssertionError")
+    except AssertionError:
+        pass

@@ -65,9 +65,10 @@ def test_collate_and_batched_entry_match_reference_fixtures():
         assert np.array_equal(v.cpu().numpy(), ref[k]), k
 
 
+@pytest.mark.parametrize("planner", ["native", "python"])
 @pytest.mark.parametrize("binomial", [False, True])
 @pytest.mark.parametrize("P,gh,gw,b,T", [(448, 5, 5, 4, 8), (64, 5, 6, 16, 8), (32, 9, 7, 8, 20)])
-def test_batched_trajectories_match_oracle(binomial, P, gh, gw, b, T):
+def test_batched_trajectories_match_oracle(planner, binomial, P, gh, gw, b, T):
     """cfg 1 (2240x2240, P=448, T=8, B=4) and smaller-patch batches, seeded, against the oracle's
     serial loop (supervised.py:116-136).  Images of one batch differ in size in the last case."""
     from jolineedle_b200.env.simple_env import generate_trajectories
@@ -91,7 +92,8 @@ def test_batched_trajectories_match_oracle(binomial, P, gh, gw, b, T):
                                         class_ids, P, T, 0, 3, binomial, seeds=seeds)
     random.seed(11)
     got = generate_trajectories({"image": [im.cuda() for im in images], "bboxes": [bboxes_of(r) for r in boxes],
-                                 "class_id": class_ids}, P, T, 0, 3, binomial_keypoints=binomial, seeds=seeds)
+                                 "class_id": class_ids}, P, T, 0, 3, binomial_keypoints=binomial, seeds=seeds,
+                                planner=planner)
     assert set(got) == set(want)
     for k in want:
         assert got[k].dtype == want[k].dtype and tuple(got[k].shape) == tuple(want[k].shape), k
