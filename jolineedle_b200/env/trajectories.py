@@ -297,6 +297,7 @@ def generate_trajectories(
     device=None,
     engine: str = "auto",
     planner: str = "auto",
+    zero_copy: bool = True,
 ) -> Dict[str, torch.Tensor]:
     """Batched supervised trajectories (``SupervisedTrainer.generate_trajectories``,
     supervised.py:95-136): ``batch`` holds lists ``image`` ([C,H,W] tensors), ``bboxes`` (lists
@@ -305,10 +306,14 @@ def generate_trajectories(
     CPU images are uploaded to ``device`` first (there is no CPU path)."""
     images: List[torch.Tensor] = list(batch["image"])
     if device is not None:
-        images = [im if im.is_cuda else im.to(device, non_blocking=True) for im in images]
+        # Pinned host images are NOT uploaded: a supervised episode looks at ~10 of an image's 30
+        # patches once, so the gather reads just those tiles over PCIe (zero-copy).  Pageable host
+        # images have to be staged through a full upload.
+        images = [im if (im.is_cuda or (zero_copy and im.is_pinned())) else im.to(device, non_blocking=True)
+                  for im in images]
     packed = plan_batch(batch["bboxes"], [im.shape[1] for im in images], [im.shape[2] for im in images], patch_size,
                         min_keypoints, max_keypoints, binomial_keypoints, position, seeds, planner)
-    image_set = ImageSet(images, patch_size)
+    image_set = ImageSet(images, patch_size, device=device)
     out = expand_packed(image_set, packed, max_seq_len, normalize, engine)
     out["class_id"] = torch.tensor([int(c) for c in batch["class_id"]], dtype=torch.long, device=image_set.device)
     out.pop("_ep_len")

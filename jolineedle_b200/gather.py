@@ -17,13 +17,20 @@ TIMING: Optional[list] = None
 
 
 class ImageSet:
-    def __init__(self, images: Union[torch.Tensor, Sequence[torch.Tensor]], patch_size: int):
+    def __init__(self, images: Union[torch.Tensor, Sequence[torch.Tensor]], patch_size: int, device=None):
+        """``device`` is only needed for *pinned host* images: those are not uploaded -- the
+        gather kernels read the tiles they need straight out of the page-locked host memory
+        (same pointer under unified addressing), so only glimpsed pixels ever cross PCIe."""
         slabs: List[torch.Tensor] = [images] if isinstance(images, torch.Tensor) else list(images)
         if not slabs:
             raise ValueError("empty image set")
         norm = []
+        self.host_mapped = False
         for t in slabs:
-            _cabi.require_cuda(t, "images")
+            if not t.is_cuda:
+                if device is None or not t.is_pinned():
+                    _cabi.require_cuda(t, "images")
+                self.host_mapped = True
             if t.dim() == 3:
                 t = t.unsqueeze(0)
             if t.dim() != 4:
@@ -32,9 +39,14 @@ class ImageSet:
                 t = t.contiguous()
             norm.append(t)
         first = norm[0]
-        self.device, self.dtype, self.channels = first.device, first.dtype, first.shape[1]
+        self.device = torch.device(device) if self.host_mapped else first.device
+        if self.device.type != "cuda":
+            raise _cabi.NativeLibraryError(f"image sets live on a CUDA device, got {self.device}")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.dtype, self.channels = first.dtype, first.shape[1]
         for t in norm:
-            if t.device != self.device or t.dtype != self.dtype or t.shape[1] != self.channels:
+            if (t.is_cuda and t.device != self.device) or t.dtype != self.dtype or t.shape[1] != self.channels:
                 raise ValueError("all images of a set must share device, dtype and channel count")
         self.patch_size = int(patch_size)
         self._slabs = norm  # keeps the memory alive

@@ -176,3 +176,30 @@ def test_full_size_round_trip_lard_shape(dtype, normalize):
         if dtype == torch.float32 or normalize:
             f = s.gather(pos[:64], src_index=src[:64], normalize=normalize, focus=True, engine=engine)
             assert torch.equal(f, focus_restatement(tiles[:64])), engine
+
+
+@pytest.mark.parametrize("engine", ["ldg", "bulk", "tensor"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.uint8])
+def test_zero_copy_gather_from_pinned_host_memory(engine, dtype):
+    """Pinned host images are gathered in place (no upload): only the glimpsed tiles cross PCIe."""
+    from jolineedle_b200.gather import ImageSet
+
+    P, gh, gw, b = 64, 3, 4, 5
+    imgs = make_images(b, gh * P, gw * P, dtype, salt=11)
+    normalize = dtype == torch.uint8
+    rng = np.random.default_rng(2)
+    pos = torch.from_numpy(np.stack([rng.integers(0, gh, b), rng.integers(0, gw, b)], 1).astype(np.int64))
+    want = ref_gather(list(imgs), pos, None, P, normalize, False)
+    # one pinned batch tensor
+    s = ImageSet(imgs.pin_memory(), P, device="cuda")
+    assert s.host_mapped
+    assert torch.equal(s.gather(pos.cuda(), normalize=normalize, engine=engine).cpu(), want)
+    # a list of separately pinned images (the DataLoader case)
+    if engine != "tensor":
+        s2 = ImageSet([im.clone().pin_memory() for im in imgs], P, device="cuda")
+        assert torch.equal(s2.gather(pos.cuda(), normalize=normalize, engine=engine).cpu(), want)
+    # pageable host memory is refused
+    from jolineedle_b200 import _cabi
+
+    with pytest.raises(_cabi.NativeLibraryError):
+        ImageSet(imgs.clone(), P, device="cuda")

@@ -140,3 +140,26 @@ def test_large_batch_properties_cfg2_shape():
             else:
                 assert float(out["patches"][i, t].abs().sum()) == 0.0
     assert int(out["next_actions"].max()) <= 7  # STOP never appears as a best action
+
+
+def test_zero_copy_batch_from_pinned_host_images_matches_device_resident():
+    """The end-to-end path of bench.py: pinned host images in, same tensors out as with resident images."""
+    from jolineedle_b200.env.simple_env import generate_trajectories
+
+    P, gh, gw, b, T = 64, 5, 6, 12, 8
+    images = [to_f32(synth_u8(1, 3, gh * P, gw * P, salt=i)[0]) for i in range(b)]
+    rng = np.random.default_rng(4)
+    boxes = []
+    for i in range(b):
+        x1, y1 = int(rng.integers(0, gw * P - 80)), int(rng.integers(0, gh * P - 80))
+        boxes.append(bboxes_of([(x1, y1, x1 + int(rng.integers(8, 80)), y1 + int(rng.integers(8, 80)))]))
+    batch_dev = {"image": [im.cuda() for im in images], "bboxes": boxes, "class_id": [0] * b}
+    batch_host = {"image": [im.pin_memory() for im in images], "bboxes": boxes, "class_id": [0] * b}
+    random.seed(5)
+    a = generate_trajectories(batch_dev, P, T, 0, 3, True, seeds=list(range(b)))
+    random.seed(5)
+    z = generate_trajectories(batch_host, P, T, 0, 3, True, seeds=list(range(b)), device="cuda")
+    random.seed(5)
+    u = generate_trajectories(batch_host, P, T, 0, 3, True, seeds=list(range(b)), device="cuda", zero_copy=False)
+    for k in a:
+        assert torch.equal(a[k], z[k]) and torch.equal(a[k], u[k]), k
