@@ -96,6 +96,7 @@ struct jn_images {
   long long image_stride = 0;
   // several slabs
   jnk::ImageRec* d_recs = nullptr;
+  bool owns_recs = true;
   CUtensorMap* d_maps = nullptr;
   // engines
   bool bulk_ok = false, tensor_ok = false;
@@ -236,7 +237,7 @@ int jn_selftest_host(float* unit_out /*HOST [256]*/, int* direction_out /*HOST [
 // ------------------------------------------------------------------------------------------
 int jn_images_create(jn_images** out, int n_slabs, const void* const* slab_ptrs, const int32_t* counts,
                      const int32_t* heights, const int32_t* widths, int channels, int dtype, int patch_size,
-                     void* stream) {
+                     void* table_dev, void* stream) {
   JN_REQUIRE(out != nullptr, "jn_images_create: out is NULL");
   *out = nullptr;
   JN_REQUIRE(n_slabs >= 1 && slab_ptrs && counts && heights && widths, "jn_images_create: empty image set");
@@ -280,11 +281,17 @@ int jn_images_create(jn_images** out, int n_slabs, const void* const* slab_ptrs,
         r.height = heights[k]; r.width = widths[k]; r.map_index = k; r.plane0 = i * channels;
         recs.push_back(r);
       }
-    if (cudaMalloc(&s->d_recs, recs.size() * sizeof(jnk::ImageRec)) != cudaSuccess)
+    if (table_dev) {
+      // caller-owned scratch (stream-ordered allocator of the host framework): no cudaMalloc /
+      // cudaFree, hence no device-wide synchronisation per batch
+      s->d_recs = static_cast<jnk::ImageRec*>(table_dev);
+      s->owns_recs = false;
+    } else if (cudaMalloc(&s->d_recs, recs.size() * sizeof(jnk::ImageRec)) != cudaSuccess) {
       return bail(fail(JN_ERR_CUDA, "cudaMalloc(image records) failed: %s", cudaGetErrorString(cudaGetLastError())));
+    }
+    // pageable source: the runtime stages the bytes before returning, so `recs` may die right after
     if (cudaMemcpyAsync(s->d_recs, recs.data(), recs.size() * sizeof(jnk::ImageRec), cudaMemcpyHostToDevice,
-                        (cudaStream_t)stream) != cudaSuccess ||
-        cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess)
+                        (cudaStream_t)stream) != cudaSuccess)
       return bail(fail(JN_ERR_CUDA, "upload of image records failed: %s", cudaGetErrorString(cudaGetLastError())));
   }
   *out = s;
@@ -293,7 +300,7 @@ int jn_images_create(jn_images** out, int n_slabs, const void* const* slab_ptrs,
 
 void jn_images_destroy(jn_images* s) {
   if (!s) return;
-  if (s->d_recs) cudaFree(s->d_recs);
+  if (s->d_recs && s->owns_recs) cudaFree(s->d_recs);
   if (s->d_maps) cudaFree(s->d_maps);
   delete s;
 }
@@ -501,6 +508,15 @@ int jn_env_step(const int64_t* pos_in, const int64_t* actions, int64_t* pos_out,
              "jn_env_step: NULL pointer");
   DeviceInfo dev;
   if (int rc = current_device_info(dev)) return rc;
+  const bool aligned16 = reinterpret_cast<uintptr_t>(pos_in) % 16 == 0 && reinterpret_cast<uintptr_t>(pos_out) % 16 == 0;
+  if (jn_bitmap_words(rows, cols) == 1 && aligned16 && pos_in != pos_out) {
+    // one-word bitmaps: a lane per episode keeps all 32 lanes of a warp busy
+    jnk::env_step_lane_kernel<<<grid_for(n, 128, dev.sm_count * 16), 128, 0, (cudaStream_t)stream>>>(
+        pos_in, actions, pos_out, visited, bbox, steps, has_stopped, rewards, terminated, truncated, n, rows, cols,
+        max_ep_len, cost, stop_enabled, status);
+    JN_CUDA(cudaGetLastError());
+    return JN_OK;
+  }
   const int wpb = 4;
   jnk::env_step_kernel<<<grid_for(n, wpb, dev.sm_count * 16), wpb * 32, 0, (cudaStream_t)stream>>>(
       pos_in, actions, pos_out, visited, bbox, steps, has_stopped, rewards, terminated, truncated, n, rows, cols,

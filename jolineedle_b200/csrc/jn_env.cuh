@@ -230,6 +230,46 @@ __global__ void env_step_kernel(const int64_t* __restrict__ pos_in, const int64_
   }
 }
 
+// Single-word grids (rows*cols <= 32, e.g. the 5x6 LARD grid of cfg 2/3): the whole bitmap of an
+// episode is one register, so a *lane* owns an episode and a warp steps 32 of them with every lane
+// busy (the warp-per-episode kernel above would idle 31 lanes in its bitmap loop and its scalar
+// tail).  Same arithmetic, same order of operations.
+__global__ void env_step_lane_kernel(const int64_t* __restrict__ pos_in, const int64_t* __restrict__ actions,
+                                     int64_t* __restrict__ pos_out, uint32_t* __restrict__ visited,
+                                     const uint32_t* __restrict__ bbox, int64_t* __restrict__ steps,
+                                     uint8_t* __restrict__ has_stopped, float* __restrict__ rewards,
+                                     uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, int n, int rows,
+                                     int cols, int max_ep_len, float cost, int stop_enabled,
+                                     int32_t* __restrict__ status) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    long long a = actions[e];
+    const bool valid = (a >= 0 && a <= kStop);
+    if (!valid) {
+      if (status) atomicOr(status, 2);
+      a = kStop;
+    }
+    const longlong2 p = reinterpret_cast<const longlong2*>(pos_in)[e];  // (y, x), 16-byte aligned rows
+    const long long y = lmin(lmax(p.x + kActionDy[a], 0), rows - 1);
+    const long long x = lmin(lmax(p.y + kActionDx[a], 0), cols - 1);
+    const bool stopped = (has_stopped[e] != 0) || (valid && a == kStop);
+    const uint32_t m = 1u << (int)(y * cols + x);
+    const uint32_t v = visited[e], b = bbox[e];
+    const int found = __popc(v & b), every = __popc(b);  // from the map BEFORE marking
+    const bool fresh = (b & m) != 0 && (v & m) == 0;
+    const uint32_t v_new = v | m;
+    visited[e] = v_new;
+    float r = __fadd_rn(fresh ? 1.0f : 0.0f, cost);
+    if (stop_enabled) r = __fadd_rn(r, (float)(stopped ? (found == every ? found : found - every) : 0));
+    rewards[e] = r;
+    const long long s = steps[e] + 1;
+    steps[e] = s;
+    has_stopped[e] = stopped ? 1 : 0;
+    truncated[e] = s >= max_ep_len ? 1 : 0;
+    terminated[e] = stop_enabled ? (stopped ? 1 : 0) : ((b & ~v_new) == 0 ? 1 : 0);
+    reinterpret_cast<longlong2*>(pos_out)[e] = make_longlong2(y, x);
+  }
+}
+
 __global__ void env_props_kernel(const uint32_t* __restrict__ visited, const uint32_t* __restrict__ bbox,
                                  const uint8_t* __restrict__ has_stopped, int n, int words, int stop_enabled,
                                  float* __restrict__ prop_patches, uint8_t* __restrict__ terminated) {

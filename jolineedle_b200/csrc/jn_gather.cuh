@@ -20,7 +20,7 @@
 
 namespace jnk {
 
-struct ImageRec {        // one per image when the set has several slabs
+struct ImageRec {        // one per image when the set has several slabs (<= 32 bytes: jn_images_table_bytes)
   const uint8_t* base;   // first byte of this image's channel 0
   int32_t height, width; // pixels
   int32_t map_index;     // tensor map of the slab this image lives in

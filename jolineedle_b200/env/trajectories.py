@@ -236,8 +236,12 @@ def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normaliz
                      out=out["patches"].view((n * T,) + out["patches"].shape[2:]), normalize=normalize,
                      engine=engine, status=status, tag="trajectory")
     # detection patches: every box patch + one random empty patch per image (simple_env.py:397-441)
-    out["patches_yolox"] = image_set.gather(d_det_pos, src_index=d_det_src, normalize=normalize, engine=engine,
-                                            status=status, tag="detection")
+    # (the buffer is sized to a multiple of 64 tiles so that torch's caching allocator can reuse it from
+    # batch to batch although the number of detection patches varies; the result is a view of its head)
+    det_cap = -(-max(n_det, 1) // 64) * 64
+    det_buf = torch.empty(image_set.out_shape(det_cap, False), dtype=torch.float32, device=dev)
+    out["patches_yolox"] = image_set.gather(d_det_pos, src_index=d_det_src, out=det_buf[:n_det], normalize=normalize,
+                                            engine=engine, status=status, tag="detection")
     det_boxes = torch.empty((n_det, n_max, 6), dtype=torch.float32, device=dev)
     if n_max > 0 and n_det > 0:
         with torch.cuda.device(dev):
@@ -315,7 +319,8 @@ def generate_trajectories(
                         min_keypoints, max_keypoints, binomial_keypoints, position, seeds, planner)
     image_set = ImageSet(images, patch_size, device=device)
     out = expand_packed(image_set, packed, max_seq_len, normalize, engine)
-    out["class_id"] = torch.tensor([int(c) for c in batch["class_id"]], dtype=torch.long, device=image_set.device)
+    class_id = np.array([int(c) for c in batch["class_id"]], dtype=np.int64)
+    out["class_id"] = torch.from_numpy(class_id).to(image_set.device, non_blocking=True)  # no stream sync
     out.pop("_ep_len")
     out.pop("_status")
     return out

@@ -24,46 +24,54 @@ class ImageSet:
         slabs: List[torch.Tensor] = [images] if isinstance(images, torch.Tensor) else list(images)
         if not slabs:
             raise ValueError("empty image set")
-        norm = []
+        # one pass over the tensors: this runs once per batch with hundreds of images, keep it lean
+        norm, counts, heights, widths, ptrs = [], [], [], [], []
         self.host_mapped = False
+        first = slabs[0]
+        dtype, cuda_device = first.dtype, None
+        channels = first.shape[-3]
         for t in slabs:
-            if not t.is_cuda:
+            if t.is_cuda:
+                if cuda_device is None:
+                    cuda_device = t.device
+                elif t.device != cuda_device:
+                    raise ValueError("all images of a set must share device, dtype and channel count")
+            else:
                 if device is None or not t.is_pinned():
                     _cabi.require_cuda(t, "images")
                 self.host_mapped = True
-            if t.dim() == 3:
-                t = t.unsqueeze(0)
-            if t.dim() != 4:
-                raise ValueError(f"images must be [C,H,W] or [B,C,H,W], got shape {tuple(t.shape)}")
+            shape = t.shape
+            if len(shape) == 3:
+                shape = (1,) + tuple(shape)
+            elif len(shape) != 4:
+                raise ValueError(f"images must be [C,H,W] or [B,C,H,W], got shape {tuple(shape)}")
+            if t.dtype != dtype or shape[1] != channels:
+                raise ValueError("all images of a set must share device, dtype and channel count")
             if not t.is_contiguous():
                 t = t.contiguous()
             norm.append(t)
-        first = norm[0]
-        self.device = torch.device(device) if self.host_mapped else first.device
+            counts.append(shape[0]); heights.append(shape[2]); widths.append(shape[3]); ptrs.append(t.data_ptr())
+        self.device = torch.device(device) if (self.host_mapped or cuda_device is None) else cuda_device
         if self.device.type != "cuda":
             raise _cabi.NativeLibraryError(f"image sets live on a CUDA device, got {self.device}")
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        self.dtype, self.channels = first.dtype, first.shape[1]
-        for t in norm:
-            if (t.is_cuda and t.device != self.device) or t.dtype != self.dtype or t.shape[1] != self.channels:
-                raise ValueError("all images of a set must share device, dtype and channel count")
+        if cuda_device is not None and cuda_device != self.device:
+            raise ValueError(f"images live on {cuda_device} but the set was asked for {self.device}")
+        self.dtype, self.channels = dtype, channels
         self.patch_size = int(patch_size)
         self._slabs = norm  # keeps the memory alive
-        self.counts = [t.shape[0] for t in norm]
-        self.n_images = sum(self.counts)
-        self.heights = [t.shape[2] for t in norm]
-        self.widths = [t.shape[3] for t in norm]
+        self.counts, self.heights, self.widths = counts, heights, widths
+        self.n_images = sum(counts)
         n = len(norm)
-        ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in norm])
-        counts = (ctypes.c_int32 * n)(*self.counts)
-        heights = (ctypes.c_int32 * n)(*self.heights)
-        widths = (ctypes.c_int32 * n)(*self.widths)
+        # per-image table of multi-slab sets: torch-owned scratch (stream-ordered), not cudaMalloc
+        self._table = torch.empty(32 * self.n_images, dtype=torch.uint8, device=self.device) if n > 1 else None
         handle = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             rc = _cabi.lib().jn_images_create(
-                ctypes.byref(handle), n, ptrs, counts, heights, widths, self.channels,
-                _cabi.dtype_code(self.dtype), self.patch_size, _cabi.stream_ptr(self.device),
+                ctypes.byref(handle), n, (ctypes.c_void_p * n)(*ptrs), (ctypes.c_int32 * n)(*counts),
+                (ctypes.c_int32 * n)(*heights), (ctypes.c_int32 * n)(*widths), channels,
+                _cabi.dtype_code(dtype), self.patch_size, _cabi.ptr(self._table), _cabi.stream_ptr(self.device),
             )
         # same precondition as the reference envs: sizes must be multiples of the patch size
         _cabi.check(rc, invalid_exc=AssertionError)
