@@ -86,10 +86,13 @@ typedef struct jn_images jn_images;
 int jn_images_create(jn_images** out, int n_slabs, const void* const* slab_ptrs /*HOST*/,
                      const int32_t* counts /*HOST*/, const int32_t* heights /*HOST*/,
                      const int32_t* widths /*HOST*/, int channels, int dtype /*jn_dtype*/,
-                     int patch_size, void* table_dev, void* stream);
-/* `table_dev`: optional caller-owned device scratch of jn_images_table_bytes(total images) bytes
- * for the per-image table of multi-slab sets (kept alive by the caller as long as the set); NULL =
- * the library allocates it (cudaMalloc / cudaFree, which synchronise the device). */
+                     int patch_size, void* table_host /*HOST*/, void* table_dev, void* stream);
+/* Multi-slab sets keep a per-image table (jn_images_table_bytes(total images) bytes) in device
+ * memory.  With `table_host` and `table_dev` both given, the library only WRITES the table into
+ * the caller's host scratch `table_host`; the caller copies it to `table_dev` on its stream before
+ * the first gather and keeps both alive as long as the set (no CUDA memory call is made, nothing
+ * synchronises).  With both NULL the library allocates and uploads the table itself
+ * (cudaMalloc / cudaFree synchronise the device). */
 static inline int64_t jn_images_table_bytes(int64_t n_images) { return n_images * 32; }
 void jn_images_destroy(jn_images* set);
 /* 1 if the TMA engines can serve this set (16-byte aligned bases / rows / patches), else 0. */

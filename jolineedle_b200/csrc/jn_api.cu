@@ -237,7 +237,7 @@ int jn_selftest_host(float* unit_out /*HOST [256]*/, int* direction_out /*HOST [
 // ------------------------------------------------------------------------------------------
 int jn_images_create(jn_images** out, int n_slabs, const void* const* slab_ptrs, const int32_t* counts,
                      const int32_t* heights, const int32_t* widths, int channels, int dtype, int patch_size,
-                     void* table_dev, void* stream) {
+                     void* table_host, void* table_dev, void* stream) {
   JN_REQUIRE(out != nullptr, "jn_images_create: out is NULL");
   *out = nullptr;
   JN_REQUIRE(n_slabs >= 1 && slab_ptrs && counts && heights && widths, "jn_images_create: empty image set");
@@ -281,18 +281,21 @@ int jn_images_create(jn_images** out, int n_slabs, const void* const* slab_ptrs,
         r.height = heights[k]; r.width = widths[k]; r.map_index = k; r.plane0 = i * channels;
         recs.push_back(r);
       }
-    if (table_dev) {
-      // caller-owned scratch (stream-ordered allocator of the host framework): no cudaMalloc /
-      // cudaFree, hence no device-wide synchronisation per batch
+    if (table_host && table_dev) {
+      // Caller-owned scratch: the table is written into `table_host` here and the CALLER copies it
+      // to `table_dev` on its stream before the first gather (with its own pinned-memory
+      // bookkeeping).  No cudaMalloc / cudaFree / memcpy in the library: nothing synchronises.
+      memcpy(table_host, recs.data(), recs.size() * sizeof(jnk::ImageRec));
       s->d_recs = static_cast<jnk::ImageRec*>(table_dev);
       s->owns_recs = false;
-    } else if (cudaMalloc(&s->d_recs, recs.size() * sizeof(jnk::ImageRec)) != cudaSuccess) {
-      return bail(fail(JN_ERR_CUDA, "cudaMalloc(image records) failed: %s", cudaGetErrorString(cudaGetLastError())));
+    } else {
+      if (cudaMalloc(&s->d_recs, recs.size() * sizeof(jnk::ImageRec)) != cudaSuccess)
+        return bail(fail(JN_ERR_CUDA, "cudaMalloc(image records) failed: %s", cudaGetErrorString(cudaGetLastError())));
+      // pageable source: the runtime stages the bytes before returning, so `recs` may die right after
+      if (cudaMemcpyAsync(s->d_recs, recs.data(), recs.size() * sizeof(jnk::ImageRec), cudaMemcpyHostToDevice,
+                          (cudaStream_t)stream) != cudaSuccess)
+        return bail(fail(JN_ERR_CUDA, "upload of image records failed: %s", cudaGetErrorString(cudaGetLastError())));
     }
-    // pageable source: the runtime stages the bytes before returning, so `recs` may die right after
-    if (cudaMemcpyAsync(s->d_recs, recs.data(), recs.size() * sizeof(jnk::ImageRec), cudaMemcpyHostToDevice,
-                        (cudaStream_t)stream) != cudaSuccess)
-      return bail(fail(JN_ERR_CUDA, "upload of image records failed: %s", cudaGetErrorString(cudaGetLastError())));
   }
   *out = s;
   return JN_OK;

@@ -163,6 +163,16 @@ def plan_native(boxes: np.ndarray, n_boxes: np.ndarray, n_max: int, rows: np.nda
 # ---------------------------------------------------------------------------------------------------
 # device half
 # ---------------------------------------------------------------------------------------------------
+def _upload(array: np.ndarray, device) -> torch.Tensor:
+    """Host array -> device through torch's pinned-memory cache: a truly asynchronous copy (a
+    pageable source would make the copy wait for the stream, serialising host planning of batch
+    i+1 behind the gathers of batch i)."""
+    staged = torch.empty(array.shape, dtype=torch.from_numpy(array[:0]).dtype, pin_memory=True)
+    staged.numpy()[...] = array
+    return staged.to(device, non_blocking=True)
+
+
+
 def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normalize: bool = False,
                   engine: str = "auto") -> Dict[str, torch.Tensor]:
     """Packed plans -> the collated sample dict of the reference (keys ``patches``,
@@ -180,9 +190,7 @@ def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normaliz
                           p.cols, p.n_boxes, det_src])
     u8 = np.concatenate([p.seg_flags, p.draws, np.zeros(1, dtype=np.uint8)])
     i64 = np.concatenate([p.boxes.ravel(), p.det_yx.astype(np.int64).ravel()])
-    d_i32 = torch.from_numpy(i32).to(dev, non_blocking=True)
-    d_u8 = torch.from_numpy(u8).to(dev, non_blocking=True)
-    d_i64 = torch.from_numpy(i64).to(dev, non_blocking=True)
+    d_i32, d_u8, d_i64 = (_upload(a, dev) for a in (i32, u8, i64))
 
     o = 0
 
@@ -320,7 +328,7 @@ def generate_trajectories(
     image_set = ImageSet(images, patch_size, device=device)
     out = expand_packed(image_set, packed, max_seq_len, normalize, engine)
     class_id = np.array([int(c) for c in batch["class_id"]], dtype=np.int64)
-    out["class_id"] = torch.from_numpy(class_id).to(image_set.device, non_blocking=True)  # no stream sync
+    out["class_id"] = _upload(class_id, image_set.device)
     out.pop("_ep_len")
     out.pop("_status")
     return out

@@ -65,14 +65,22 @@ class ImageSet:
         self.n_images = sum(counts)
         n = len(norm)
         # per-image table of multi-slab sets: torch-owned scratch (stream-ordered), not cudaMalloc
-        self._table = torch.empty(32 * self.n_images, dtype=torch.uint8, device=self.device) if n > 1 else None
+        # (written by the library into pinned host scratch, uploaded here with torch so that the pinned
+        # block is not recycled before the copy has run; no cudaMalloc / cudaFree / sync per batch)
+        self._table = self._table_host = None
+        if n > 1:
+            self._table_host = torch.empty(32 * self.n_images, dtype=torch.uint8, pin_memory=True)
+            self._table = torch.empty(32 * self.n_images, dtype=torch.uint8, device=self.device)
         handle = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             rc = _cabi.lib().jn_images_create(
                 ctypes.byref(handle), n, (ctypes.c_void_p * n)(*ptrs), (ctypes.c_int32 * n)(*counts),
                 (ctypes.c_int32 * n)(*heights), (ctypes.c_int32 * n)(*widths), channels,
-                _cabi.dtype_code(dtype), self.patch_size, _cabi.ptr(self._table), _cabi.stream_ptr(self.device),
+                _cabi.dtype_code(dtype), self.patch_size, _cabi.ptr(self._table_host), _cabi.ptr(self._table),
+                _cabi.stream_ptr(self.device),
             )
+            if rc == _cabi.JN_OK and self._table is not None:
+                self._table.copy_(self._table_host, non_blocking=True)
         # same precondition as the reference envs: sizes must be multiples of the patch size
         _cabi.check(rc, invalid_exc=AssertionError)
         self._handle = handle

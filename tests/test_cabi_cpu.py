@@ -48,7 +48,7 @@ def test_invalid_arguments_are_reported_not_crashed():
     one = (ctypes.c_int32 * 1)(1)
     h = (ctypes.c_int32 * 1)(100)
     w = (ctypes.c_int32 * 1)(96)
-    rc = lib.jn_images_create(ctypes.byref(handle), 1, ptrs, one, h, w, 3, _cabi.JN_F32, 16, None, None)
+    rc = lib.jn_images_create(ctypes.byref(handle), 1, ptrs, one, h, w, 3, _cabi.JN_F32, 16, None, None, None)
     assert rc == _cabi.JN_ERR_INVALID  # 100 is not a multiple of 16
     assert b"multiple of patch_size" in lib.jn_last_error()
     with pytest.raises(AssertionError):
