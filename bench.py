@@ -83,7 +83,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark(self, name):
+        setattr(self, name, time.perf_counter())
 
     def __exit__(self, *exc):
         if self.proc is not None:
@@ -95,11 +98,21 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        # samples taken inside the timed region (the sampler itself runs from before the warm-up, so that
+        # nvidia-smi's start-up does not land in the timed steps); if the region was shorter than the sampling
+        # period, the two samples that bracket it
+        t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", float("inf"))
+        inside = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.3]
+        if not inside:
+            before = [r for (t, r) in self.rows if t < t0][-1:]
+            after = [r for (t, r) in self.rows if t > t1][:1]
+            inside = before + after
+        rows = [r for r in inside if len(r) >= 9]
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for name, v in zip(names, r[5:9]):
                     if v.lower().startswith("active"):
@@ -295,7 +308,7 @@ def reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="supervised", choices=sorted(WORKLOADS))
@@ -303,6 +316,9 @@ def main():
     ap.add_argument("--src", default="f32", choices=["f32", "u8"], help="resident image dtype")
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-pool", type=int, default=0,
+                    help="distinct pinned host images per rank in the e2e arm (default: all of them up to 2 ranks, "
+                         "64 beyond, to bound page-locked host memory at 8 ranks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -341,15 +357,18 @@ def main():
     peak, peak_kind = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
 
     # ---- device-resident arm ------------------------------------------------------------------
-    for s in range(args.warmup):
-        wl.run(s)
-    barrier()
-    gather.TIMING = []
-    units = torch.zeros((), dtype=torch.float64, device=device)
-    valid = []
-    launches0 = _cabi.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
+        for s in range(args.warmup):
+            wl.run(s)
+        barrier()
+        time.sleep(0.6)  # let nvidia-smi finish initialising (NVML start-up stalls CUDA calls) before timing
+        gather.TIMING = []
+        units = torch.zeros((), dtype=torch.float64, device=device)
+        valid = []
+        launches0 = _cabi.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        clocks.mark("t0")
         ev0.record()
         for s in range(args.steps):
             out = wl.run(args.warmup + s)
@@ -358,6 +377,7 @@ def main():
             valid.append(g)
         ev1.record()
         barrier()
+        clocks.mark("t1")
     launches = _cabi.launch_count() - launches0
     timing, gather.TIMING = gather.TIMING, None
     ms = max_over_ranks(ev0.elapsed_time(ev1), device)
@@ -383,10 +403,15 @@ def main():
     # ---- end-to-end arm: HOST buffers in, host-visible results out ---------------------------------
     e2e = None
     if not args.no_e2e:
+        def pinned(t):
+            return torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
+
         if args.workload == "supervised":
-            host = [img.cpu().pin_memory() for img in wl.images]
+            pool = args.e2e_pool or (wl.batch if world <= 2 else 64)
+            distinct = [pinned(img) for img in wl.images[:pool]]
+            host = [distinct[i % len(distinct)] for i in range(wl.batch)]
         else:
-            host = wl.images.cpu().pin_memory()
+            host = pinned(wl.images)
         full = sum(t.numel() * t.element_size() for t in host) if isinstance(host, list) else host.numel() * host.element_size()
         zero_copy = args.workload == "supervised"  # pinned lists are gathered in place; batched RL images are uploaded
         e2e_steps = max(2, min(args.steps, 5))
@@ -412,7 +437,8 @@ def main():
                else "uploaded inside the timed region")
         e2e = {"value": sum_over_ranks(eunits, device) / (ems / 1e3), "unit": "gaze-steps/s",
                "h2d_bytes_per_step": int(h2d / e2e_steps), "d2h_bytes_per_step": int(d2h_bytes), "steps": e2e_steps,
-               "host_buffers": f"pinned {src} images ({full} bytes resident on the host), {how}"}
+               "host_buffers": f"pinned {src} images ({full} bytes addressed on the host"
+                               + (f", {len(distinct)} distinct" if zero_copy else "") + f"), {how}"}
         del host
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ------------------------------------------------
