@@ -348,6 +348,8 @@ def main():
     cls, default_batch = WORKLOADS[args.workload]
     src = args.src if args.workload == "supervised" else "u8"
     wl = cls(args.batch or default_batch, rank, device, src)
+    # nvidia-smi is started here, seconds before the timed region: its NVML start-up stalls CUDA calls
+    clocks = ClockSampler(local_rank).__enter__()
     wl.to_device()
     peaks = {}
     try:
@@ -357,11 +359,10 @@ def main():
     peak, peak_kind = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
 
     # ---- device-resident arm ------------------------------------------------------------------
-    with ClockSampler(local_rank) as clocks:
+    try:
         for s in range(args.warmup):
             wl.run(s)
         barrier()
-        time.sleep(0.6)  # let nvidia-smi finish initialising (NVML start-up stalls CUDA calls) before timing
         gather.TIMING = []
         units = torch.zeros((), dtype=torch.float64, device=device)
         valid = []
@@ -370,14 +371,19 @@ def main():
         barrier()
         clocks.mark("t0")
         ev0.record()
+        step_host = [time.perf_counter()]
         for s in range(args.steps):
             out = wl.run(args.warmup + s)
             g = wl.gaze_steps(out)
             units += g
             valid.append(g)
+            step_host.append(time.perf_counter())
         ev1.record()
         barrier()
         clocks.mark("t1")
+    finally:
+        clocks.__exit__(None, None, None)
+    host_ms = [round(1e3 * (b - a), 2) for a, b in zip(step_host, step_host[1:])]
     launches = _cabi.launch_count() - launches0
     timing, gather.TIMING = gather.TIMING, None
     ms = max_over_ranks(ev0.elapsed_time(ev1), device)
@@ -467,7 +473,7 @@ def main():
                              "writes GBs of crops",
                        "parallelism": f"episodes sharded over {world} GPU(s), no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks.summary(),
+            "clocks": clocks.summary(), "host_ms_per_step": host_ms,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
