@@ -244,9 +244,11 @@ def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normaliz
                      out=out["patches"].view((n * T,) + out["patches"].shape[2:]), normalize=normalize,
                      engine=engine, status=status, tag="trajectory")
     # detection patches: every box patch + one random empty patch per image (simple_env.py:397-441)
-    # (the buffer is sized to a multiple of 64 tiles so that torch's caching allocator can reuse it from
-    # batch to batch although the number of detection patches varies; the result is a view of its head)
-    det_cap = -(-max(n_det, 1) // 64) * 64
+    # (the buffer is sized to a whole number of tiles per image so that torch's caching allocator can
+    # reuse it from batch to batch although the number of detection patches varies -- a fresh multi-GB
+    # cudaMalloc costs tens of milliseconds; the result is a view of the buffer's head)
+    quantum = max(n, 64)
+    det_cap = -(-max(n_det, 1) // quantum) * quantum
     det_buf = torch.empty(image_set.out_shape(det_cap, False), dtype=torch.float32, device=dev)
     out["patches_yolox"] = image_set.gather(d_det_pos, src_index=d_det_src, out=det_buf[:n_det], normalize=normalize,
                                             engine=engine, status=status, tag="detection")
