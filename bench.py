@@ -197,11 +197,11 @@ class SupervisedWorkload:
 class ReinforceWorkload:
     name = ("cfg3 reinforce: LARD-shaped 2240x2688 (padded), patch 448, max-seq-len 20, enable-stop, seeded random "
             "actions, uint8-resident images normalised on gather")
-    T = 20
+    T, PATCH, GRID = 20, P, (GH, GW)
 
     def __init__(self, batch, rank, device, src_dtype):
         self.batch, self.rank, self.device, self.src_dtype = batch, rank, device, src_dtype
-        self.h, self.w = GH * P, GW * P
+        self.h, self.w = self.GRID[0] * self.PATCH, self.GRID[1] * self.PATCH
         rng = np.random.default_rng(4321 + rank)
         raw = synth_boxes(rng, batch, self.h, self.w)
         nmax = max(len(r) for r in raw)
@@ -219,8 +219,8 @@ class ReinforceWorkload:
         from jolineedle_b200.reinforce import rollout_tail
 
         imgs = self.images if images is None else images
-        env = NeedleGeneralEnv(imgs, self.boxes, P, self.T, 1, stop_enabled=True, normalize=(self.src_dtype == "u8"),
-                               history=True, device=device)
+        env = NeedleGeneralEnv(imgs, self.boxes, self.PATCH, self.T, 1, stop_enabled=True,
+                               normalize=(self.src_dtype == "u8"), history=True, device=device)
         torch.manual_seed(step * 31 + self.rank)
         self.gen.manual_seed(step * 31 + self.rank)
         b = self.batch
@@ -241,7 +241,7 @@ class ReinforceWorkload:
 
     def gather_bytes(self, n_items, valid_items, tag):
         s_in = 1 if self.src_dtype == "u8" else 4
-        return n_items * 3 * P * P * (s_in + 4)
+        return n_items * 3 * self.PATCH * self.PATCH * (s_in + 4)
 
     def d2h(self, out):
         host = {k: out[k].cpu() for k in ("rewards", "returns", "masks")}
@@ -259,7 +259,7 @@ class ReinforceWorkload:
         rng = np.random.default_rng(step)
         torch.manual_seed(step)
         t0 = time.perf_counter()
-        env = GazeOracle(imgs, boxes, P, self.T, 1, True, raster_masks=True)
+        env = GazeOracle(imgs, boxes, self.PATCH, self.T, 1, True, raster_masks=True)
         env.reset()
         rew, term = [], []
         for t in range(self.T):
@@ -271,7 +271,14 @@ class ReinforceWorkload:
         return float(n_episodes * (self.T + 1)), dt
 
 
-WORKLOADS = {"supervised": (SupervisedWorkload, 256), "reinforce": (ReinforceWorkload, 1024)}
+class AerialWorkload(ReinforceWorkload):
+    name = ("cfg4 aerial: 8192x8192 synthetic images, patch 256 (32x32 grid, 1024-bit bitmaps), max-seq-len 32, "
+            "enable-stop, seeded random actions, uint8-resident images normalised on gather")
+    T, PATCH, GRID = 32, 256, (32, 32)
+
+
+WORKLOADS = {"supervised": (SupervisedWorkload, 256), "reinforce": (ReinforceWorkload, 1024),
+             "aerial": (AerialWorkload, 96)}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -282,7 +289,7 @@ def reference_arm(args, rank, world):
         return
     torch.set_num_threads(os.cpu_count() or 1)
     cls, default_batch = WORKLOADS[args.workload]
-    sample = args.cpu_sample or (24 if args.workload == "supervised" else 8)
+    sample = args.cpu_sample or {"supervised": 24, "reinforce": 8, "aerial": 2}[args.workload]
     wl = cls(sample, 0, "cpu", "f32")
     for s in range(args.warmup):
         wl.cpu_sample(sample, s)
@@ -346,7 +353,7 @@ def main():
         torch.cuda.synchronize(device)
 
     cls, default_batch = WORKLOADS[args.workload]
-    src = args.src if args.workload == "supervised" else "u8"
+    src = args.src if args.workload == "supervised" else "u8"  # RL workloads keep uint8-resident images
     wl = cls(args.batch or default_batch, rank, device, src)
     # nvidia-smi is started here, seconds before the timed region: its NVML start-up stalls CUDA calls
     clocks = ClockSampler(local_rank).__enter__()
@@ -455,7 +462,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
-        sample = args.cpu_sample or (32 if args.workload == "supervised" else 8)
+        sample = args.cpu_sample or {"supervised": 32, "reinforce": 8, "aerial": 2}[args.workload]
         reps = 8 if args.workload == "supervised" else 3
         wl.cpu_sample(sample, 0)
         u_sum, t_sum = 0.0, 0.0

@@ -202,3 +202,30 @@ def test_large_batch_properties_cfg3_shape():
                 assert torch.equal(patches[i, 0], want)
     assert torch.equal(env.visited_patches, visited_ref)
     env.check_status()
+
+
+def test_cfg4_geometry_8192_patch256_seq32():
+    """BASELINE cfg 4 geometry: 8192x8192 images, P=256 -> 32x32 grid (1024-bit bitmaps: one word per
+    lane in the warp-per-episode step kernel), T=32, STOP enabled; against the oracle, uint8-resident."""
+    b, P, g_, T = 2, 256, 32, 32
+    gen = torch.Generator().manual_seed(44)
+    u8 = torch.randint(0, 256, (b, 3, g_ * P, g_ * P), dtype=torch.uint8, generator=gen)
+    images = u8.float() / 255
+    rng = np.random.default_rng(8)
+    boxes = random_boxes(rng, b, 4, g_ * P, g_ * P, 700)
+    orc = GazeOracle(images, boxes, P, T, 1, True)
+    env = make_env(u8.cuda(), torch.from_numpy(boxes), P, T, 1, True, normalize=True)
+    assert np.array_equal(env.bbox_masks.cpu().numpy(), orc.bbox_masks)
+    torch.manual_seed(3); p_o, i_o = orc.reset()
+    torch.manual_seed(3); p_e, i_e = env.reset()
+    assert torch.equal(p_e.cpu(), p_o) and np.array_equal(i_e["positions"].cpu().numpy(), i_o["positions"])
+    for t in range(T):
+        # walk towards / over the first box so that rewards and the found-all branch are exercised
+        a = rng.integers(0, 9, size=b).astype(np.int64) if t % 3 else np.array([7, 4], dtype=np.int64)
+        o, e = orc.step(a), env.step(torch.from_numpy(a))
+        assert torch.equal(e[0].cpu(), o[0]), t
+        assert np.array_equal(e[1].cpu().numpy(), o[1]) and np.array_equal(e[2].cpu().numpy(), o[2])
+        assert np.array_equal(e[3].cpu().numpy(), o[3]) and np.array_equal(e[4]["positions"].cpu().numpy(), o[4]["positions"])
+    assert np.array_equal(env.visited_patches.cpu().numpy(), orc.visited)
+    assert np.array_equal(env.prop_patches_found.cpu().numpy(), orc.prop_patches_found())
+    env.check_status()
