@@ -304,6 +304,70 @@ class NeedleSimpleEnv:
             self._plan_walk(plan, keypoint, keypoint, first)
         return plan
 
+    # -- incremental sample API (the reference's eval loop fills a sample step by step) ------------------
+    def init_sample(self, max_ep_len: int, device=None) -> dict:
+        """Zeroed sample buffers plus the detection patches (simple_env.py:378-441).  Consumes one
+        ``rng.choice`` like the reference; tensors live on the image's CUDA device."""
+        s = self._ensure_set()
+        dev, p, n = s.device, self.patch_size, len(self.raw_bboxes)
+        sample = {
+            "patches": torch.zeros((max_ep_len, self.n_channels, p, p), dtype=torch.float, device=dev),
+            "current_actions": torch.zeros((max_ep_len,), dtype=torch.long, device=dev),
+            "next_actions": torch.zeros((max_ep_len,), dtype=torch.long, device=dev),
+            "positions": torch.zeros((max_ep_len, 2), dtype=torch.long, device=dev),
+            "masks": torch.zeros((max_ep_len,), dtype=torch.float, device=dev),
+            "labels": torch.zeros((max_ep_len,), dtype=torch.long, device=dev),
+            "local_bboxes": torch.zeros((max_ep_len, n, 6), device=dev),
+        }
+        det: Set[Position] = set()
+        for box in self.raw_bboxes:
+            for c in self.bbox_positions(box):
+                det.add(c)
+        empties = [Position(y, x) for y, x in product(range(self.patch_height), range(self.patch_width))
+                   if Position(y, x) not in det]
+        if empties:
+            det.add(empties[self.rng.choice(len(empties))])
+        cells = list(det)
+        if cells:
+            pos = torch.tensor([[int(c[0]), int(c[1])] for c in cells], dtype=torch.long, device=dev)
+            src = torch.zeros((len(cells),), dtype=torch.int32, device=dev)
+            sample["patches_yolox"] = s.gather(pos, src_index=src, normalize=self._normalize).float()
+            sample["bboxes_yolox"] = torch.stack([self.local_bboxes(c) for c in cells]).to(dev)
+        else:  # fictitious entry (simple_env.py:421-436)
+            sample["patches_yolox"] = torch.zeros((1, self.n_channels, p, p), dtype=torch.float, device=dev)
+            sample["bboxes_yolox"] = torch.zeros((1, n, 6), dtype=torch.float, device=dev)
+        return sample
+
+    def add_to_sample(self, sample: dict, action_taken: Action, patch: torch.Tensor, infos: dict, index: int):
+        """Record one step (simple_env.py:443-479); buffers double in length when full."""
+        if sample["patches"].shape[0] <= index:
+            for key in sample:
+                if key in ("patches_yolox", "bboxes_yolox"):
+                    continue
+                sample[key] = torch.cat([sample[key], torch.zeros_like(sample[key])], dim=0)
+        sample["patches"][index] = patch
+        sample["current_actions"][index] = action_taken.value
+        sample["next_actions"][index] = infos["best_action"].value
+        sample["positions"][index, 0] = int(infos["position"][0])
+        sample["positions"][index, 1] = int(infos["position"][1])
+        sample["masks"][index] = 1.0
+        sample["labels"][index] = int(infos["inside_bbox"])
+        sample["local_bboxes"][index] = infos["local_bboxes"].to(sample["local_bboxes"].device)
+
+    def best_next_action(self, position: Optional[Position] = None,
+                         visited_bbox_patches: Optional[Set[Position]] = None) -> Action:
+        """The expert's next action from ``position``: what the reference's eval loop obtains by generating a
+        whole 50-step ``generate_sample(50, 0, 0, position, visited)`` and reading ``next_actions[0]``
+        (supervised.py:301-309,340-348).  Only the host plan is made here -- no buffer, no pixel -- and the
+        same random draws are consumed (one ``random.choice`` per greedy key point, the ``rng`` calls of the
+        plan), so interleaving it with the reference's call order keeps both streams in step."""
+        plan = self.plan_sample(0, 0, False, position, visited_bbox_patches)
+        target = plan.seg_tgt[0]
+        code = direction_code(target[0] - plan.start[0], target[1] - plan.start[1])
+        if code == STOP_CODE:
+            code = plan.draws[0]
+        return Action(code)
+
     def generate_sample(
         self,
         max_ep_len: int,

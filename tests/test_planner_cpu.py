@@ -181,3 +181,37 @@ def test_native_planner_unseeded_and_unsupported_inputs():
         raise RuntimeError("expected AssertionError")
     except AssertionError:
         pass
+
+
+def test_best_next_action_equals_reference_eval_oracle():
+    """supervised.py:301-309: the expert action = next_actions[0] of a fresh 50-step sample generated from the
+    current position / visited set.  The host-only shortcut must give the same action and leave both random
+    streams (python's global one and the env's numpy generator) where the reference call leaves them."""
+    import copy
+    import random
+
+    from oracle.traj_oracle import Pos, TrajectoryOracle
+
+    fx = load_golden("simple_env.npz")
+    rng = np.random.default_rng(0)
+    checked = 0
+    for name in fx["names"]:
+        c, cfg = simple_case(fx, str(name))
+        boxes = c["raw_boxes"].tolist()
+        env = make_env(c, cfg)
+        orc = TrajectoryOracle(to_f32(c["u8"]), cfg["P"], [((y1, x1), (y2, x2)) for (x1, y1, x2, y2) in boxes],
+                               seed=cfg["seed"])
+        gh, gw = env.patch_height, env.patch_width
+        for _ in range(4):
+            pos = (int(rng.integers(0, gh)), int(rng.integers(0, gw)))
+            visited = {p for p in sorted(env.bbox_patches) if rng.random() < 0.3}
+            random.seed(checked)
+            want = int(orc.generate_sample(50, 0, 0, False, Pos(*pos), {Pos(*v) for v in visited})["next_actions"][0])
+            state_ref, np_ref = random.getstate(), orc.rng.bit_generator.state
+            random.seed(checked)
+            got = env.best_next_action(Position(*pos), {Position(*v) for v in visited})
+            assert got.value == want, (name, pos)
+            assert random.getstate() == state_ref
+            assert env.rng.bit_generator.state == np_ref
+            checked += 1
+    assert checked >= 100

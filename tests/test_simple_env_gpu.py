@@ -163,3 +163,45 @@ def test_zero_copy_batch_from_pinned_host_images_matches_device_resident():
     u = generate_trajectories(batch_host, P, T, 0, 3, True, seeds=list(range(b)), device="cuda", zero_copy=False)
     for k in a:
         assert torch.equal(a[k], z[k]) and torch.equal(a[k], u[k]), k
+
+
+def test_incremental_sample_api_matches_oracle():
+    """The eval loop of the reference (supervised.py:280-360) drives the env step by step:
+    reset -> init_sample -> add_to_sample -> step ...; deepcopy(env) must work too."""
+    from copy import deepcopy
+
+    from jolineedle_b200.env.common import Action
+    from jolineedle_b200.env.simple_env import NeedleSimpleEnv
+    from jolineedle_b200.utils import Position
+    from oracle.traj_oracle import Pos, TrajectoryOracle
+
+    fx = load_golden("simple_env.npz")
+    for name in ("s03", "s10", "s21"):
+        c, cfg = simple_case(fx, name)
+        raw = c["raw_boxes"].tolist()
+        img = to_f32(c["u8"])
+        env = NeedleSimpleEnv(img.cuda(), cfg["P"], bboxes_of(raw), seed=cfg["seed"])
+        orc = TrajectoryOracle(img, cfg["P"], [((y1, x1), (y2, x2)) for (x1, y1, x2, y2) in raw], seed=cfg["seed"])
+        cpy = deepcopy(env)
+        assert cpy.image is env.image and cpy.bbox_patches == env.bbox_patches and cpy.bbox_patches is not env.bbox_patches
+        T = 5
+        patch, infos = env.reset(Position(1, 1))
+        o_patch, o_infos = orc.reset(Pos(1, 1))
+        assert torch.equal(patch.cpu(), o_patch) and infos["inside_bbox"] == o_infos["inside_bbox"]
+        sample = env.init_sample(T, "cuda")
+        o_sample = orc._blank_sample(T)
+        infos["best_action"] = Action.LEFT
+        env.add_to_sample(sample, Action.LEFT, patch, infos, 0)
+        orc._record(o_sample, 0, 0, o_patch, o_infos, 0)
+        moves = [1, 3, 7, 0, 2, 5, 3]  # more steps than T: the buffers must double
+        for i, m in enumerate(moves, start=1):
+            patch, infos = env.step(Action(m))
+            o_patch, o_infos = orc.step(m)
+            assert infos["position"] == tuple(o_infos["position"]) and infos["number_patches_found"] == o_infos["number_patches_found"]
+            assert torch.equal(infos["local_bboxes"], o_infos["local_bboxes"])
+            infos["best_action"] = Action((m + 1) % 8)
+            env.add_to_sample(sample, Action(m), patch, infos, i)
+            orc._record(o_sample, i, m, o_patch, o_infos, (m + 1) % 8)
+        for k in ("patches", "current_actions", "next_actions", "positions", "masks", "labels", "local_bboxes",
+                  "patches_yolox", "bboxes_yolox"):
+            assert sample[k].dtype == o_sample[k].dtype and torch.equal(sample[k].cpu(), o_sample[k]), (name, k)
