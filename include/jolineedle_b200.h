@@ -112,12 +112,18 @@ int jn_images_tma_ok(const jn_images* set, int engine /*jn_engine*/);
  * plus the per-step copy into the sample (simple_env.py:472), the patch loop of
  * get_detection_batch (general_env.py:531-542) and of init_sample (simple_env.py:417-419).
  *
+ * `shifts` (device int32 [n_images, 2] = (ty, tx) per image, or NULL): the tiles are taken from the
+ * image translated by (tx, ty) pixels with zero fill -- tile pixel (r, c) of patch (y, x) is image
+ * pixel (y*P + r - ty, x*P + c - tx) -- i.e. the integer `translate` augmentation of the reference's
+ * dataset (dataset.py:157-226, torchvision F.affine with fill 0) folded into the gather instead of
+ * materialising a shifted copy of the image.  TMA path for one slab and P <= 256, plain loads else.
+ *
  * `status` (device int32[1], may be NULL) is OR-ed with 1 if some position was outside the
  * patch grid (that tile is skipped).
  * ------------------------------------------------------------------------------------------ */
 int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src_index,
-              int n_items, void* out, int64_t out_item_stride_bytes, uint32_t flags,
-              int engine /*jn_engine*/, int32_t* status, void* stream);
+              const int32_t* shifts, int n_items, void* out, int64_t out_item_stride_bytes,
+              uint32_t flags, int engine /*jn_engine*/, int32_t* status, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K0  patch x bbox overlap tables.

@@ -39,7 +39,7 @@ SIGNATURES = {
                                  POINTER(c_int32), c_int, c_int, c_int, _P, _P, _P]),
     "jn_images_destroy": (None, [_P]),
     "jn_images_tma_ok": (c_int, [_P, c_int]),
-    "jn_gather": (c_int, [_P, _P, _P, c_int, _P, c_int64, c_uint32, c_int, _P, _P]),
+    "jn_gather": (c_int, [_P, _P, _P, _P, c_int, _P, c_int64, c_uint32, c_int, _P, _P]),
     "jn_patch_bitmaps": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, _P]),
     "jn_bitmap_unpack": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "jn_split_boxes": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),

@@ -126,9 +126,22 @@ int pick_rows(int patch, int elem, int target_bytes, bool need_even) {
 }
 
 int encode_slab_map(CUtensorMap* map, const void* ptr, int elem, int n_planes, int height, int width, int box_w,
-                    int kbox, int rows) {
+                    int kbox, int rows, bool three_d = false) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return fail(JN_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  if (three_d) {
+    // 3-D view [W] x [H] x [planes], box = [patch] x [rows] x 1: element-granular x / y offsets (used by
+    // translated gathers; pixels outside the image are zero-filled by the TMA unit)
+    cuuint64_t dims3[3] = {(cuuint64_t)width, (cuuint64_t)height, (cuuint64_t)n_planes};
+    cuuint64_t strides3[2] = {(cuuint64_t)width * elem, (cuuint64_t)width * elem * height};
+    cuuint32_t box3[3] = {(cuuint32_t)(box_w * kbox), (cuuint32_t)rows, 1};
+    cuuint32_t estr3[3] = {1, 1, 1};
+    const CUtensorMapDataType dt3 = elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+    CUresult r3 = fn(map, dt3, 3, const_cast<void*>(ptr), dims3, strides3, box3, estr3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r3 != CUDA_SUCCESS) return fail(JN_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r3);
+    return JN_OK;
+  }
   // 4-D view (innermost first): [box_w] x [width / box_w] x [height] x [planes]
   cuuint64_t dims[4] = {(cuuint64_t)box_w, (cuuint64_t)(width / box_w), (cuuint64_t)height, (cuuint64_t)n_planes};
   cuuint64_t strides[3] = {(cuuint64_t)box_w * elem, (cuuint64_t)width * elem, (cuuint64_t)width * elem * height};
@@ -318,8 +331,9 @@ int jn_images_tma_ok(const jn_images* s, int engine) {
 // ------------------------------------------------------------------------------------------
 // K1 gather
 // ------------------------------------------------------------------------------------------
-int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src_index, int n_items, void* out,
-              int64_t out_item_stride_bytes, uint32_t flags, int engine, int32_t* status, void* stream_) {
+int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src_index, const int32_t* shifts,
+              int n_items, void* out, int64_t out_item_stride_bytes, uint32_t flags, int engine, int32_t* status,
+              void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   JN_REQUIRE(set != nullptr, "jn_gather: image set is NULL");
   JN_REQUIRE(n_items >= 0, "jn_gather: negative item count");
@@ -341,7 +355,7 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
   jnk::GatherArgs a;
   memset(&a, 0, sizeof(a));
   a.base = set->base; a.images = set->d_recs; a.maps = nullptr;
-  a.positions = positions; a.src_index = src_index;
+  a.positions = positions; a.src_index = src_index; a.shifts = shifts;
   a.out = static_cast<uint8_t*>(out); a.out_item_stride = out_item_stride_bytes; a.image_stride = set->image_stride;
   a.status = status; a.n_items = n_items; a.n_images = set->n_images;
   a.channels = C; a.height = set->height; a.width = set->width; a.patch = P; a.elem = set->elem;
@@ -351,10 +365,19 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
   const bool out_aligned = reinterpret_cast<uintptr_t>(out) % 16 == 0 && out_item_stride_bytes % 16 == 0;
   // u8 -> u8 Focus has no TMA kernel (nobody asks for it); it runs on the LDG engine.
   const bool tma_mode = plain_copy || normalize || (focus && set->dtype == JN_F32);
+  // Translated sources need arbitrary element offsets and zero fill outside the image: that is the
+  // 3-D tensor map with one box per row block (patch <= 256 elements, single slab); anything else
+  // goes to the plain-load engine.
+  const bool shift_tensor_ok = set->tensor_ok && set->n_slabs == 1 && set->kbox == 1;
   if (engine == JN_ENGINE_AUTO) {
     if (!tma_mode || !out_aligned || !set->bulk_ok) engine = JN_ENGINE_LDG;
+    else if (shifts) engine = shift_tensor_ok ? JN_ENGINE_TENSOR : JN_ENGINE_LDG;
     else engine = (set->tensor_ok && set->n_slabs == 1) ? JN_ENGINE_TENSOR : JN_ENGINE_BULK;
   }
+  if (shifts && engine == JN_ENGINE_TENSOR)
+    JN_REQUIRE(shift_tensor_ok, "translated gathers on the tensor engine need one slab and patch_size <= 256");
+  if (shifts && engine == JN_ENGINE_BULK)
+    return fail(JN_ERR_INVALID, "the bulk engine cannot translate (needs 16-byte aligned row starts); use auto");
   if (engine == JN_ENGINE_TENSOR)
     JN_REQUIRE(tma_mode && out_aligned && set->tensor_ok && set->n_slabs == 1,
                "tensor-map engine unavailable for this image set / flags (needs one slab, 16-byte aligned rows)");
@@ -385,7 +408,7 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
   memset(&map, 0, sizeof(map));
   if (engine == JN_ENGINE_TENSOR) {
     if (int rc = encode_slab_map(&map, set->base, set->elem, set->n_images * C, set->height, set->width, set->box_w,
-                                 set->kbox, rows))
+                                 set->kbox, rows, shifts != nullptr))
       return rc;
   }
 

@@ -124,6 +124,14 @@ __device__ __forceinline__ void tensor_g2s_4d(void* dst_smem, const CUtensorMap*
       "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void tensor_g2s_3d(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2,
+                                              uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], "
+      "[%5];" ::"r"(smem_u32(dst_smem)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }

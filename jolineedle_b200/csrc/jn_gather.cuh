@@ -33,6 +33,7 @@ struct GatherArgs {
   const CUtensorMap* maps;    // multi-slab sets, tensor engine: tensor maps (device memory)
   const int64_t* positions;   // [n_items, 2] (y, x) patch coordinates
   const int32_t* src_index;   // [n_items] image per item (negative = zero fill) or null = identity
+  const int32_t* shifts;      // [n_images, 2] (ty, tx) integer translation of each image (zero fill) or null
   uint8_t* out;
   long long out_item_stride;  // bytes
   long long image_stride;     // single slab: bytes between images
@@ -51,6 +52,7 @@ struct Chunk {
   long long src_row_bytes;
   int item, channel, row0;  // tile-local first row
   int map_index, plane, px, py;
+  int sy, sx;  // translation of the source image: tile pixel (r, c) <- image pixel (py*P + r - sy, px*P + c - sx)
 };
 
 // Decode chunk q.  Out-of-grid positions are reported once and treated as "skip" (src = null,
@@ -83,6 +85,8 @@ __device__ __forceinline__ bool decode_chunk(const GatherArgs& a, int q, Chunk& 
     return true;  // skip
   }
   c.px = (int)x; c.py = (int)y;
+  c.sy = a.shifts ? a.shifts[2 * img] : 0;
+  c.sx = a.shifts ? a.shifts[2 * img + 1] : 0;
   c.src_row_bytes = (long long)w * a.elem;
   c.src = base + (((long long)c.channel * h + y * a.patch + c.row0) * w + x * a.patch) * a.elem;
   return false;
@@ -131,7 +135,10 @@ gather_copy_kernel(const __grid_constant__ GatherArgs a, const __grid_constant__
           if (lane == 0) {
             const CUtensorMap* m = a.maps ? a.maps + c.map_index : &map0;
             if (a.maps) fence_tensormap_acquire(m);
-            tensor_g2s_4d(stage, m, 0, c.px * a.kbox, c.py * a.patch + c.row0, c.plane, &full[st]);
+            if (a.shifts)  // 3-D map [W, H, planes]: arbitrary element offsets, out-of-image pixels arrive as zeros
+              tensor_g2s_3d(stage, m, c.px * a.patch - c.sx, c.py * a.patch + c.row0 - c.sy, c.plane, &full[st]);
+            else
+              tensor_g2s_4d(stage, m, 0, c.px * a.kbox, c.py * a.patch + c.row0, c.plane, &full[st]);
           }
         } else {
           for (int r = lane; r < a.rows; r += 32)
@@ -251,7 +258,10 @@ gather_xform_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
           if (lane == 0) {
             const CUtensorMap* m = a.maps ? a.maps + c.map_index : &map0;
             if (a.maps) fence_tensormap_acquire(m);
-            tensor_g2s_4d(stage, m, 0, c.px * a.kbox, c.py * a.patch + c.row0, c.plane, &full[st]);
+            if (a.shifts)  // 3-D map [W, H, planes]: arbitrary element offsets, out-of-image pixels arrive as zeros
+              tensor_g2s_3d(stage, m, c.px * a.patch - c.sx, c.py * a.patch + c.row0 - c.sy, c.plane, &full[st]);
+            else
+              tensor_g2s_4d(stage, m, 0, c.px * a.kbox, c.py * a.patch + c.row0, c.plane, &full[st]);
           }
         } else {
           for (int r = lane; r < a.rows; r += 32)
@@ -307,12 +317,18 @@ __global__ void gather_ldg_kernel(const GatherArgs a, const int out_f32, const i
         if (a.status && rem == 0 && ch == 0) atomicOr(a.status, 1);
         continue;
       }
-      const long long e = ((long long)ch * h + y * P + r) * w + x * P + col;
-      if (a.elem == 4) {
-        fv = reinterpret_cast<const float*>(base)[e];
-      } else {
-        bv = base[e];
-        fv = normalize ? u8_to_unit((float)bv) : (float)bv;
+      const long long sy = y * P + r - (a.shifts ? a.shifts[2 * img] : 0);
+      const long long sx = x * P + col - (a.shifts ? a.shifts[2 * img + 1] : 0);
+      if (sy >= 0 && sy < h && sx >= 0 && sx < w) {  // outside the (translated) image: zero fill
+        const long long e = ((long long)ch * h + sy) * w + sx;
+        if (a.elem == 4) {
+          fv = reinterpret_cast<const float*>(base)[e];
+        } else {
+          bv = base[e];
+          fv = normalize ? u8_to_unit((float)bv) : (float)bv;
+        }
+      } else if (normalize) {
+        fv = 0.f;
       }
     }
     long long o;

@@ -13,6 +13,10 @@ Extensions (keyword-only, default = reference behaviour):
   history    pre-allocate ``[B, max_ep_len + 1, C, P, P]`` and write step t's crops into slot
              t + 1 (``patch_history(t)`` then replaces the caller's per-step ``torch.concat``,
              reinforce.py:175-179)
+  translate  ``[B, 2]`` integer ``(tx, ty)`` per image: crops come from the image shifted by that many
+             pixels with zero fill -- the ``--augment-translate`` augmentation (dataset.py:157-226,
+             ``F.affine(translate=[tx, ty], fill=0)``) folded into the gather coordinates instead of a
+             shifted copy of the image made on the CPU.  The caller shifts the boxes (as the dataset does).
   device     upload CPU inputs to this CUDA device (the reference keeps everything on
              ``images.device``; there is no CPU path here)
 """
@@ -41,6 +45,7 @@ class NeedleGeneralEnv:
         history: bool = False,
         engine: str = "auto",
         device=None,
+        translate: Optional[Tensor] = None,
     ):
         # same preconditions as general_env.py:37-39,50-51
         assert images.shape[0] == bboxes.shape[0]
@@ -65,6 +70,12 @@ class NeedleGeneralEnv:
         self.n_horizontal_patches = self.width // self.patch_size
         self.device = images.device
         self._normalize, self._focus, self._engine = normalize, focus, engine
+        self._shifts = None
+        if translate is not None:
+            t = torch.as_tensor(translate)
+            assert tuple(t.shape) == (self.batch_size, 2), "translate must be [batch_size, 2] = (tx, ty) per image"
+            # kernels take (ty, tx)
+            self._shifts = t.to(torch.int32).flip(1).contiguous().to(self.device)
 
         self._set = ImageSet(images, patch_size)
         # [B, G=1, C, H, W] view of the caller's tensor (callers read env.images[0, 0])
@@ -139,7 +150,7 @@ class NeedleGeneralEnv:
         if self._history is not None:
             out = self._history[:, self._t]
         patches = self._set.gather(self.positions, out=out, normalize=self._normalize, focus=self._focus,
-                                   engine=self._engine, status=self._status, tag="step")
+                                   engine=self._engine, status=self._status, tag="step", shifts=self._shifts)
         return patches.unsqueeze(1)  # [B, G=1, C, P, P]
 
     @property

@@ -113,6 +113,7 @@ class ImageSet:
         engine: str = "auto",
         status: Optional[torch.Tensor] = None,
         tag: str = "",
+        shifts: Optional[torch.Tensor] = None,
     ) -> torch.Tensor:
         """Tile ``positions[i] = (y, x)`` of image ``src_index[i]`` (default ``i``; negative =
         zeros) -> ``out[i]``.  ``out`` may be any tensor whose ``out[i]`` is contiguous (e.g. a
@@ -126,6 +127,11 @@ class ImageSet:
             if src_index.dtype != torch.int32 or src_index.numel() != n:
                 raise ValueError("src_index must be an int32 tensor with one entry per position")
             src_index = src_index.contiguous()
+        if shifts is not None:
+            # per-image integer translation (ty, tx) with zero fill, see jn_gather in the header
+            if shifts.dtype != torch.int32 or tuple(shifts.shape) != (self.n_images, 2) or shifts.device != self.device:
+                raise ValueError(f"shifts must be an int32 [{self.n_images}, 2] tensor of (ty, tx) on {self.device}")
+            shifts = shifts.contiguous()
         shape, dtype = self.out_shape(n, focus), self.out_dtype(normalize)
         if out is None:
             out = torch.empty(shape, dtype=dtype, device=self.device)
@@ -142,7 +148,8 @@ class ImageSet:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
             rc = _cabi.lib().jn_gather(
-                self._handle, positions.data_ptr(), _cabi.ptr(src_index), n, out.data_ptr(), stride, flags,
+                self._handle, positions.data_ptr(), _cabi.ptr(src_index), _cabi.ptr(shifts), n, out.data_ptr(), stride,
+                flags,
                 _cabi.ENGINES[engine], _cabi.ptr(status), _cabi.stream_ptr(self.device),
             )
             if timing is not None:

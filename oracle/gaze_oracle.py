@@ -272,3 +272,20 @@ def returns_oracle_numpy(rewards: np.ndarray, logit_masks: np.ndarray) -> np.nda
             acc = acc + np.float64(term)
             out[i, s] = np.float32(acc)
     return out
+
+
+def translate_oracle(images: torch.Tensor, shifts_xy) -> torch.Tensor:
+    """Integer translation with zero fill, per image: ``out[.., y, x] = in[.., y - ty, x - tx]``.
+
+    This is what the reference's dataset does for ``--augment-translate`` (dataset.py:207-214):
+    ``torchvision.transforms.functional.affine(image, angle=0, translate=[tx, ty], scale=1.0,
+    shear=0.0, fill=0.0)`` with its default nearest interpolation (checked against torchvision in
+    tests/test_oracle_cpu.py).  ``images`` is [B, C, H, W]; ``shifts_xy`` is [B, 2] = (tx, ty)."""
+    out = torch.zeros_like(images)
+    _, _, h, w = images.shape
+    for i, (tx, ty) in enumerate(np.asarray(shifts_xy).tolist()):
+        ys0, ys1 = max(0, -ty), min(h, h - ty)  # source rows that stay inside
+        xs0, xs1 = max(0, -tx), min(w, w - tx)
+        if ys0 < ys1 and xs0 < xs1:
+            out[i, :, ys0 + ty : ys1 + ty, xs0 + tx : xs1 + tx] = images[i, :, ys0:ys1, xs0:xs1]
+    return out

@@ -151,3 +151,18 @@ def test_returns_oracle_matches_reference(name):
 def test_normalisation_table():
     table = load_golden("norm.npz")["u8_over_255"]
     assert np.array_equal((torch.arange(256, dtype=torch.uint8).float() / 255).numpy(), table)
+
+
+def test_translate_oracle_equals_torchvision_affine():
+    """dataset.py:207-214 uses F.affine with an integer translation; the oracle restates it as a shift."""
+    import torchvision.transforms.functional as TF
+
+    from oracle.gaze_oracle import translate_oracle
+
+    g = torch.Generator().manual_seed(1)
+    images = torch.rand((5, 3, 40, 56), generator=g)
+    shifts = [(0, 0), (7, -3), (-11, 5), (55, 39), (-56, 2)]
+    got = translate_oracle(images, shifts)
+    for i, (tx, ty) in enumerate(shifts):
+        want = TF.affine(images[i], angle=0, translate=[tx, ty], scale=1.0, shear=0.0, fill=0.0)
+        assert torch.equal(got[i], want), (tx, ty)
