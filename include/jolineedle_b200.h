@@ -45,6 +45,7 @@ typedef enum jn_dtype { JN_U8 = 0, JN_F32 = 1 } jn_dtype;
 /* jn_gather flags */
 #define JN_GATHER_NORMALIZE 1u /* uint8 source -> float32 output, value / 255 (ToTensor, dataset.py:240) */
 #define JN_GATHER_FOCUS 2u     /* output in YOLOX Focus space-to-depth layout [4*C, P/2, P/2] */
+#define JN_GATHER_SHIFT_ALIGNED 4u /* caller guarantees every x shift is a multiple of 16 bytes (TMA may serve it) */
 
 /* jn_gather engine selection (JN_ENGINE_AUTO picks the fastest one the shapes allow) */
 typedef enum jn_engine {
@@ -116,7 +117,9 @@ int jn_images_tma_ok(const jn_images* set, int engine /*jn_engine*/);
  * image translated by (tx, ty) pixels with zero fill -- tile pixel (r, c) of patch (y, x) is image
  * pixel (y*P + r - ty, x*P + c - tx) -- i.e. the integer `translate` augmentation of the reference's
  * dataset (dataset.py:157-226, torchvision F.affine with fill 0) folded into the gather instead of
- * materialising a shifted copy of the image.  TMA path for one slab and P <= 256, plain loads else.
+ * materialising a shifted copy of the image.  Served by a plain-load kernel (one warp per tile row);
+ * the TMA unit only accepts inner offsets that are 16-byte multiples, so it is used when the caller
+ * sets JN_GATHER_SHIFT_ALIGNED (one slab, P <= 256).
  *
  * `status` (device int32[1], may be NULL) is OR-ed with 1 if some position was outside the
  * patch grid (that tile is skipped).

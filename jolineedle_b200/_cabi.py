@@ -15,7 +15,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 JN_OK, JN_ERR_INVALID, JN_ERR_CUDA, JN_ERR_UNSUPPORTED, JN_ERR_NO_DEVICE = range(5)
 JN_U8, JN_F32 = 0, 1
-GATHER_NORMALIZE, GATHER_FOCUS = 1, 2
+GATHER_NORMALIZE, GATHER_FOCUS, GATHER_SHIFT_ALIGNED = 1, 2, 4
 ENGINE_AUTO, ENGINE_TENSOR, ENGINE_BULK, ENGINE_LDG = 0, 1, 2, 3
 ENGINES = {"auto": ENGINE_AUTO, "tensor": ENGINE_TENSOR, "bulk": ENGINE_BULK, "ldg": ENGINE_LDG}
 RULE_ANY_PIXEL, RULE_AREA5 = 0, 1

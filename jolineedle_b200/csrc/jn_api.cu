@@ -368,14 +368,18 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
   // Translated sources need arbitrary element offsets and zero fill outside the image: that is the
   // 3-D tensor map with one box per row block (patch <= 256 elements, single slab); anything else
   // goes to the plain-load engine.
-  const bool shift_tensor_ok = set->tensor_ok && set->n_slabs == 1 && set->kbox == 1;
+  // The TMA unit traps (illegal instruction) on inner coordinates that are not 16-byte multiples, so it only
+  // serves translations the caller vouches for (JN_GATHER_SHIFT_ALIGNED: every tx * elem % 16 == 0).
+  const bool shift_tensor_ok = set->tensor_ok && set->n_slabs == 1 && set->kbox == 1 &&
+                               (flags & JN_GATHER_SHIFT_ALIGNED) != 0;
   if (engine == JN_ENGINE_AUTO) {
     if (!tma_mode || !out_aligned || !set->bulk_ok) engine = JN_ENGINE_LDG;
     else if (shifts) engine = shift_tensor_ok ? JN_ENGINE_TENSOR : JN_ENGINE_LDG;
     else engine = (set->tensor_ok && set->n_slabs == 1) ? JN_ENGINE_TENSOR : JN_ENGINE_BULK;
   }
   if (shifts && engine == JN_ENGINE_TENSOR)
-    JN_REQUIRE(shift_tensor_ok, "translated gathers on the tensor engine need one slab and patch_size <= 256");
+    JN_REQUIRE(shift_tensor_ok, "translated gathers on the tensor engine need one slab, patch_size <= 256 and "
+                                "JN_GATHER_SHIFT_ALIGNED (x shifts that are multiples of 16 bytes)");
   if (shifts && engine == JN_ENGINE_BULK)
     return fail(JN_ERR_INVALID, "the bulk engine cannot translate (needs 16-byte aligned row starts); use auto");
   if (engine == JN_ENGINE_TENSOR)
@@ -386,9 +390,16 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
 
   if (engine == JN_ENGINE_LDG) {
     a.rows = 1; a.chunks_per_plane = P; a.total_chunks = 0;
-    const long long total = (long long)n_items * C * P * P;
-    const int grid = grid_for(total, 256 * 8, dev.sm_count * 16);
-    jnk::gather_ldg_kernel<<<grid, 256, 0, stream>>>(a, out_elem == 4, normalize, focus);
+    const bool rows_ok = P % 4 == 0 && out_aligned && !(focus && out_elem == 1);
+    if (rows_ok) {  // one warp per tile row, 16-byte stores
+      const long long units = (long long)n_items * C * P;
+      jnk::gather_rows_kernel<<<grid_for(units, 8, dev.sm_count * 8), 256, 0, stream>>>(a, out_elem == 4, normalize,
+                                                                                         focus);
+    } else {  // any patch size / alignment: one thread per element
+      const long long total = (long long)n_items * C * P * P;
+      jnk::gather_ldg_kernel<<<grid_for(total, 256 * 8, dev.sm_count * 16), 256, 0, stream>>>(a, out_elem == 4,
+                                                                                               normalize, focus);
+    }
     JN_CUDA(cudaGetLastError());
     return JN_OK;
   }

@@ -286,6 +286,80 @@ gather_xform_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------
+// rows kernel (plain loads, one warp per tile row)
+// ------------------------------------------------------------------------------------------
+// For what TMA cannot address: source rows that do not start on a 16-byte boundary (arbitrary integer
+// translation: the TMA unit traps on inner coordinates that are not 16-byte multiples) and lists of
+// images combined with a translation.  A warp owns one row of one channel of one tile; each lane
+// loads four consecutive source pixels with scalar loads (any alignment; the warp still covers whole
+// cache lines) and writes one aligned 16-byte store (two 8-byte stores in the Focus layout).  Pixels
+// outside the translated image are zeros.  Needs P % 4 == 0 and a 16-byte aligned output.
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const GatherArgs a, const int out_f32, const int normalize, const int focus) {
+  const int P = a.patch, lane = threadIdx.x & 31;
+  const long long units = (long long)a.n_items * a.channels * P;  // (item, channel, row)
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long u = warp0; u < units; u += n_warps) {
+    const int item = (int)(u / ((long long)a.channels * P));
+    const int rem = (int)(u - (long long)item * a.channels * P);
+    const int ch = rem / P, r = rem - ch * P;
+    const int img = a.src_index ? a.src_index[item] : item;
+    const uint8_t* base = nullptr;
+    int h = 0, w = 0;
+    long long y = 0, x = 0;
+    bool zero_row = img < 0;
+    if (!zero_row) {
+      y = a.positions[2 * (long long)item]; x = a.positions[2 * (long long)item + 1];
+      if (a.images) {
+        const ImageRec rec = a.images[img];
+        base = rec.base; h = rec.height; w = rec.width;
+      } else {
+        base = a.base + (long long)img * a.image_stride; h = a.height; w = a.width;
+      }
+      if (img >= a.n_images || y < 0 || x < 0 || (y + 1) * P > h || (x + 1) * P > w) {
+        if (a.status && lane == 0 && ch == 0 && r == 0) atomicOr(a.status, 1);
+        continue;  // out-of-grid position: tile skipped
+      }
+    }
+    const long long sy = zero_row ? -1 : y * P + r - (a.shifts ? a.shifts[2 * img] : 0);
+    const long long sx0 = zero_row ? 0 : x * P - (a.shifts ? a.shifts[2 * img + 1] : 0);
+    const bool row_ok = !zero_row && sy >= 0 && sy < h;
+    const uint8_t* row = row_ok ? base + (((long long)ch * h + sy) * w) * a.elem : nullptr;
+    uint8_t* dst_item = a.out + (long long)item * a.out_item_stride;
+    for (int g = lane; g < P / 4; g += 32) {
+      float f[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t packed = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long sx = sx0 + 4 * g + k;
+        if (row_ok && sx >= 0 && sx < w) {
+          if (a.elem == 4) {
+            f[k] = reinterpret_cast<const float*>(row)[sx];
+          } else {
+            const uint32_t b = row[sx];
+            packed |= b << (8 * k);
+            f[k] = normalize ? u8_to_unit((float)b) : (float)b;
+          }
+        }
+      }
+      if (!out_f32) {  // uint8 -> uint8 (plain layout only; Focus for uint8 output stays on the element kernel)
+        reinterpret_cast<uint32_t*>(dst_item + ((long long)ch * P + r) * P)[g] = packed;
+      } else if (!focus) {
+        st_f4(reinterpret_cast<float*>(dst_item) + ((long long)ch * P + r) * P + 4 * g, f[0], f[1], f[2], f[3]);
+      } else {
+        const int half = P / 2;
+        const long long plane = (long long)half * half;
+        float* even = reinterpret_cast<float*>(dst_item) + (long long)((r & 1) * a.channels + ch) * plane +
+                      (long long)(r >> 1) * half + 2 * g;
+        st_f2(even, f[0], f[2]);
+        st_f2(even + 2ll * a.channels * plane, f[1], f[3]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // ldg kernel (element-wise fallback)
 // ------------------------------------------------------------------------------------------
 // One thread per output element of the plain layout; handles every dtype / flag combination.

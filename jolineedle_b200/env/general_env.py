@@ -70,11 +70,13 @@ class NeedleGeneralEnv:
         self.n_horizontal_patches = self.width // self.patch_size
         self.device = images.device
         self._normalize, self._focus, self._engine = normalize, focus, engine
-        self._shifts = None
+        self._shifts, self._shifts_aligned = None, False
         if translate is not None:
             t = torch.as_tensor(translate)
             assert tuple(t.shape) == (self.batch_size, 2), "translate must be [batch_size, 2] = (tx, ty) per image"
-            # kernels take (ty, tx)
+            # kernels take (ty, tx); x shifts that are all multiples of 16 bytes can ride the TMA path
+            elem = 1 if images.dtype == torch.uint8 else 4
+            self._shifts_aligned = bool(((t[:, 0].to(torch.int64) * elem) % 16 == 0).all()) if not t.is_cuda else False
             self._shifts = t.to(torch.int32).flip(1).contiguous().to(self.device)
 
         self._set = ImageSet(images, patch_size)
@@ -150,7 +152,8 @@ class NeedleGeneralEnv:
         if self._history is not None:
             out = self._history[:, self._t]
         patches = self._set.gather(self.positions, out=out, normalize=self._normalize, focus=self._focus,
-                                   engine=self._engine, status=self._status, tag="step", shifts=self._shifts)
+                                   engine=self._engine, status=self._status, tag="step", shifts=self._shifts,
+                                   shifts_aligned=self._shifts_aligned)
         return patches.unsqueeze(1)  # [B, G=1, C, P, P]
 
     @property

@@ -29,6 +29,9 @@ def test_gather_with_translation(engine, dtype, P, gh, gw):
     images = u8 if dtype == torch.uint8 else u8.float() / 255
     # (tx, ty): none, small, negative, larger than a patch, and far enough to empty whole tiles
     shifts_xy = np.array([(0, 0), (13, -7), (-P // 3, P // 5), (P + 9, -(P + 3)), (-(gw * P - 5), gh * P - 2)])
+    aligned = engine == "tensor"
+    if aligned:  # the TMA unit only takes x offsets that are multiples of 16 bytes; y is free
+        shifts_xy[:, 0] = (shifts_xy[:, 0] // 16) * 16
     shifted = translate_oracle(images, shifts_xy)
     s = ImageSet(images.cuda(), P)
     n = 24
@@ -45,11 +48,12 @@ def test_gather_with_translation(engine, dtype, P, gh, gw):
             want = table[want.long()]
         if focus:
             want = focus_restatement(want)
-        got = s.gather(pos.cuda(), src_index=src.cuda(), shifts=d_shifts, normalize=normalize, focus=focus,
-                       engine=engine)
+        got = s.gather(pos.cuda(), src_index=src.cuda(), shifts=d_shifts, shifts_aligned=aligned, normalize=normalize,
+                       focus=focus, engine=engine)
         assert torch.equal(got.cpu(), want), (engine, dtype, P, normalize, focus)
     if dtype == torch.float32:
-        got = s.gather(pos.cuda(), src_index=src.cuda(), shifts=d_shifts, focus=True, engine=engine)
+        got = s.gather(pos.cuda(), src_index=src.cuda(), shifts=d_shifts, shifts_aligned=aligned, focus=True,
+                       engine=engine)
         assert torch.equal(got.cpu(), focus_restatement(crops_of(shifted, pos, src, P)))
 
 
@@ -63,6 +67,9 @@ def test_bulk_engine_refuses_translation_and_lists_fall_back():
     shifts = torch.tensor([[5, -9], [-70, 3]], dtype=torch.int32).cuda()  # (ty, tx)
     with pytest.raises(ValueError):
         s.gather(pos, shifts=shifts, engine="bulk")
+    with pytest.raises(ValueError):  # the tensor engine needs the caller's word that x shifts are 16-byte aligned
+        ImageSet(torch.rand(2, 3, 2 * P, 2 * P).cuda(), P).gather(pos[:, :1].repeat(1, 2) * 0, shifts=shifts,
+                                                                  engine="tensor")
     got = s.gather(pos, shifts=shifts)  # auto -> plain loads for a list of images
     for i, im in enumerate(imgs):
         ty, tx = shifts[i].tolist()
