@@ -278,7 +278,7 @@ class AerialWorkload(ReinforceWorkload):
 
 
 WORKLOADS = {"supervised": (SupervisedWorkload, 256), "reinforce": (ReinforceWorkload, 1024),
-             "aerial": (AerialWorkload, 96)}
+             "aerial": (AerialWorkload, 512)}
 
 
 # ----------------------------------------------------------------------------------------------

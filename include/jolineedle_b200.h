@@ -171,6 +171,11 @@ int jn_env_step(const int64_t* pos_in, const int64_t* actions, int64_t* pos_out,
                 const uint32_t* bbox, int64_t* steps, uint8_t* has_stopped, float* rewards,
                 uint8_t* terminated, uint8_t* truncated, int n, int rows, int cols,
                 int max_ep_len, float cost, int stop_enabled, int32_t* status, void* stream);
+/* The `rewards` property evaluated on the current state, outside of a step (general_env.py:321-358):
+ * float32 [n], same arithmetic as jn_env_step but with `visited` as it is now. */
+int jn_env_rewards(const int64_t* positions, const uint32_t* visited, const uint32_t* bbox,
+                   const uint8_t* has_stopped, int n, int rows, int cols, float cost, int stop_enabled,
+                   float* rewards, void* stream);
 /* prop_patches_found (general_env.py:308-315) as float32 [n]; `terminated` (general_env.py:
  * 235-246, uint8 [n]) is written too when non-NULL. */
 int jn_env_props(const uint32_t* visited, const uint32_t* bbox, const uint8_t* has_stopped, int n,

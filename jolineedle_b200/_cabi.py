@@ -48,6 +48,7 @@ SIGNATURES = {
     "jn_env_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int,
                             _P, _P]),
     "jn_env_props": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "jn_env_rewards": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P, _P]),
     "jn_returns": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P, _P]),
     "jn_returns_rows": (c_int, [_P, c_int64, _P, c_int64, c_int, c_int, _P, _P]),
     "jn_traj_expand": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, c_int, c_int, _P, _P, _P, _P, _P, _P,
@@ -63,7 +64,7 @@ SIGNATURES = {
 # entry points that launch exactly one kernel of ours per successful call
 KERNEL_CALLS = frozenset({
     "jn_gather", "jn_patch_bitmaps", "jn_bitmap_unpack", "jn_split_boxes", "jn_local_boxes", "jn_env_reset",
-    "jn_env_step", "jn_env_props", "jn_returns", "jn_returns_rows", "jn_traj_expand",
+    "jn_env_step", "jn_env_props", "jn_env_rewards", "jn_returns", "jn_returns_rows", "jn_traj_expand",
 })
 
 

@@ -562,6 +562,19 @@ int jn_env_step(const int64_t* pos_in, const int64_t* actions, int64_t* pos_out,
   return JN_OK;
 }
 
+int jn_env_rewards(const int64_t* positions, const uint32_t* visited, const uint32_t* bbox, const uint8_t* has_stopped,
+                   int n, int rows, int cols, float cost, int stop_enabled, float* rewards, void* stream) {
+  JN_REQUIRE(n >= 0 && rows >= 1 && cols >= 1, "jn_env_rewards: bad sizes");
+  if (n == 0) return JN_OK;
+  JN_REQUIRE(positions && visited && bbox && has_stopped && rewards, "jn_env_rewards: NULL pointer");
+  DeviceInfo dev;
+  if (int rc = current_device_info(dev)) return rc;
+  jnk::env_rewards_kernel<<<grid_for(n, 128, dev.sm_count * 16), 128, 0, (cudaStream_t)stream>>>(
+      positions, visited, bbox, has_stopped, n, rows, cols, jn_bitmap_words(rows, cols), cost, stop_enabled, rewards);
+  JN_CUDA(cudaGetLastError());
+  return JN_OK;
+}
+
 int jn_env_props(const uint32_t* visited, const uint32_t* bbox, const uint8_t* has_stopped, int n, int rows, int cols,
                  int stop_enabled, float* prop_patches, uint8_t* terminated, void* stream) {
   JN_REQUIRE(n >= 0 && rows >= 1 && cols >= 1, "jn_env_props: bad sizes");

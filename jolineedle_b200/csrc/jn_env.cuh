@@ -270,6 +270,29 @@ __global__ void env_step_lane_kernel(const int64_t* __restrict__ pos_in, const i
   }
 }
 
+// The `rewards` property of the reference (general_env.py:321-358) evaluated on the CURRENT state, outside
+// of a step: fresh = bbox[pos] & ~visited[pos] with whatever `visited` holds now.  One thread per episode.
+__global__ void env_rewards_kernel(const int64_t* __restrict__ positions, const uint32_t* __restrict__ visited,
+                                   const uint32_t* __restrict__ bbox, const uint8_t* __restrict__ has_stopped, int n,
+                                   int rows, int cols, int words, float cost, int stop_enabled,
+                                   float* __restrict__ rewards) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const long long y = positions[2 * (long long)e], x = positions[2 * (long long)e + 1];
+    int found = 0, every = 0;
+    bool fresh = false;
+    const int bit = (y >= 0 && y < rows && x >= 0 && x < cols) ? (int)(y * cols + x) : -1;
+    for (int w = 0; w < words; ++w) {
+      const uint32_t v = visited[(long long)e * words + w], b = bbox[(long long)e * words + w];
+      found += __popc(v & b);
+      every += __popc(b);
+      if (bit >= 0 && (bit >> 5) == w) fresh = ((b >> (bit & 31)) & 1u) && !((v >> (bit & 31)) & 1u);
+    }
+    float r = __fadd_rn(fresh ? 1.0f : 0.0f, cost);
+    if (stop_enabled) r = __fadd_rn(r, (float)(has_stopped[e] ? (found == every ? found : found - every) : 0));
+    rewards[e] = r;
+  }
+}
+
 __global__ void env_props_kernel(const uint32_t* __restrict__ visited, const uint32_t* __restrict__ bbox,
                                  const uint8_t* __restrict__ has_stopped, int n, int words, int stop_enabled,
                                  float* __restrict__ prop_patches, uint8_t* __restrict__ terminated) {

@@ -27,7 +27,7 @@ from torch import Tensor
 
 from .. import _cabi
 from ..gather import ImageSet
-from .common import Action, ACTION_DELTAS  # noqa: F401  (re-exported like the reference module)
+from .common import Action, ACTION_DELTAS, DELTA_TABLE  # noqa: F401  (re-exported like the reference module)
 
 
 class NeedleGeneralEnv:
@@ -227,6 +227,50 @@ class NeedleGeneralEnv:
     @property
     def prop_bboxes_found(self) -> Tensor:  # general_env.py:317-319
         return (self.prop_patches_found > 0).to(torch.float32)
+
+    @property
+    def rewards(self) -> Tensor:
+        """Reward of the CURRENT state (general_env.py:321-358).  ``step`` evaluates it between the move and
+        the visited-map update; called on its own it sees whatever the visited map holds now."""
+        out = torch.empty((self.batch_size,), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.jn_env_rewards(
+                self.positions.data_ptr(), self._visited_words.data_ptr(), self._bbox_words.data_ptr(),
+                self.has_stopped.data_ptr(), self.batch_size, self.n_vertical_patches, self.n_horizontal_patches,
+                self._cost, 1 if self.stop_enabled else 0, out.data_ptr(), self._stream()))
+        return out
+
+    def convert_bboxes_to_masks(self, bboxes: Tensor) -> Tensor:
+        """``[B, rows, cols]`` bool, patch holds a pixel of some box (general_env.py:360-379), for any
+        ``[B, N, 4]`` box tensor -- the closed form of rasterise + max-pool, computed by K0."""
+        boxes = torch.as_tensor(bboxes).to(device=self.device, dtype=torch.int64).contiguous()
+        b = boxes.shape[0]
+        words = torch.empty((b, self._words), dtype=torch.int32, device=self.device)
+        out = torch.empty((b, self.n_vertical_patches, self.n_horizontal_patches), dtype=torch.bool, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.jn_patch_bitmaps(
+                boxes.data_ptr(), None, b, boxes.shape[1], self.patch_size, self.n_vertical_patches,
+                self.n_horizontal_patches, None, None, _cabi.RULE_ANY_PIXEL, words.data_ptr(), self._words,
+                self._stream()))
+            _cabi.check(self._lib.jn_bitmap_unpack(words.data_ptr(), b, self.n_vertical_patches,
+                                                   self.n_horizontal_patches, out.data_ptr(), self._stream()))
+        return out
+
+    def actions_to_movements(self, actions: Tensor) -> Tensor:
+        """``[B, 2]`` (dy, dx) of each action code (general_env.py:209-212) -- a table lookup on the
+        device instead of one ``.item()`` round trip per episode."""
+        table = torch.tensor(DELTA_TABLE, dtype=torch.long, device=actions.device)
+        return table[actions.long()]
+
+    def apply_movements(self, actions: Tensor):
+        """Move, clamp to the grid, remember STOP (general_env.py:214-233).  ``step`` does this inside K2;
+        the stand-alone method exists for callers that drive the pieces themselves."""
+        actions = actions.to(self.device)
+        moved = self.positions + self.actions_to_movements(actions)
+        moved[:, 0].clamp_(0, self.n_vertical_patches - 1)
+        moved[:, 1].clamp_(0, self.n_horizontal_patches - 1)
+        self.positions = moved
+        self.has_stopped |= actions == Action.STOP.value
 
     @property
     def tiles_reached(self) -> Tensor:  # general_env.py:248-283

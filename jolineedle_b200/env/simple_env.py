@@ -45,6 +45,18 @@ def apply_action(current_position: Position, action: Action) -> Position:
     return Position(current_position.y + dy, current_position.x + dx)
 
 
+def get_patch(image: torch.Tensor, patch_size: int, position: Position) -> torch.Tensor:
+    """``[C, P, P]`` window of patch ``position`` = (y, x) (simple_env.py:55-81).  Like the reference this is
+    a *view* of the image (no copy, no kernel); the batched paths use the K1 gather instead."""
+    _, height, width = image.shape
+    assert height % patch_size == 0
+    assert width % patch_size == 0
+    assert 0 <= position[0] < height // patch_size
+    assert 0 <= position[1] < width // patch_size
+    y, x = int(position[0]) * patch_size, int(position[1]) * patch_size
+    return image[:, y:y + patch_size, x:x + patch_size]
+
+
 class EpisodePlan:
     """Host-side description of one supervised episode (input of ``jn_traj_expand``)."""
 
@@ -218,6 +230,21 @@ class NeedleSimpleEnv:
 
     def remove_stop_action(self, action: Action) -> Action:  # simple_env.py:715-718
         return self.rng.choice(MOVES) if action == Action.STOP else action
+
+    def visit_point(self, sample: dict, to_visit: Position, true_target: Position, device: str = "cpu"):
+        """Walk straight to ``to_visit`` recording every step into ``sample`` (simple_env.py:631-664), for
+        callers that build samples incrementally; ``generate_sample`` itself plans the walk on the host and
+        expands it on the device.  The recorded best action points at ``true_target`` (a random move
+        replaces STOP); the visited set is cleared after each step, as in the reference."""
+        self.reset(self.position)
+        index = int(sample["masks"].long().sum().item())
+        while self.position != to_visit:
+            action = move_towards(self.position, to_visit)
+            patch, infos = self.step(action)
+            infos["best_action"] = self.remove_stop_action(move_towards(self.position, true_target))
+            self._place(self.position, None)
+            self.add_to_sample(sample, action, patch, infos, index)
+            index += 1
 
     def build_keypoints_trajectory(self) -> List[Position]:
         """Greedy nearest-first (L1) order of the unvisited box patches; ties through python's
