@@ -278,7 +278,7 @@ class AerialWorkload(ReinforceWorkload):
 
 
 WORKLOADS = {"supervised": (SupervisedWorkload, 256), "reinforce": (ReinforceWorkload, 1024),
-             "aerial": (AerialWorkload, 512)}
+             "aerial": (AerialWorkload, 256)}  # 256 x 201 MB uint8 = 48 GiB resident (+ the same again in the e2e arm)
 
 
 # ----------------------------------------------------------------------------------------------

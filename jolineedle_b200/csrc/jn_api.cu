@@ -97,7 +97,6 @@ struct jn_images {
   // several slabs
   jnk::ImageRec* d_recs = nullptr;
   bool owns_recs = true;
-  CUtensorMap* d_maps = nullptr;
   // engines
   bool bulk_ok = false, tensor_ok = false;
   int box_w = 0, kbox = 0;
@@ -291,7 +290,7 @@ int jn_images_create(jn_images** out, int n_slabs, const void* const* slab_ptrs,
       for (int i = 0; i < counts[k]; ++i) {
         jnk::ImageRec r;
         r.base = static_cast<const uint8_t*>(slab_ptrs[k]) + (long long)i * channels * heights[k] * widths[k] * elem;
-        r.height = heights[k]; r.width = widths[k]; r.map_index = k; r.plane0 = i * channels;
+        r.height = heights[k]; r.width = widths[k]; r.slab = k; r.plane0 = i * channels;
         recs.push_back(r);
       }
     if (table_host && table_dev) {
@@ -317,7 +316,6 @@ int jn_images_create(jn_images** out, int n_slabs, const void* const* slab_ptrs,
 void jn_images_destroy(jn_images* s) {
   if (!s) return;
   if (s->d_recs && s->owns_recs) cudaFree(s->d_recs);
-  if (s->d_maps) cudaFree(s->d_maps);
   delete s;
 }
 
@@ -354,7 +352,7 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
 
   jnk::GatherArgs a;
   memset(&a, 0, sizeof(a));
-  a.base = set->base; a.images = set->d_recs; a.maps = nullptr;
+  a.base = set->base; a.images = set->d_recs;
   a.positions = positions; a.src_index = src_index; a.shifts = shifts;
   a.out = static_cast<uint8_t*>(out); a.out_item_stride = out_item_stride_bytes; a.image_stride = set->image_stride;
   a.status = status; a.n_items = n_items; a.n_images = set->n_images;

@@ -135,11 +135,6 @@ __device__ __forceinline__ void tensor_g2s_3d(void* dst_smem, const CUtensorMap*
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
-// Tensor maps that live in global memory (image sets with several slabs) were written by the
-// host before the launch; the acquire fence makes them visible to the tensormap proxy.
-__device__ __forceinline__ void fence_tensormap_acquire(const CUtensorMap* map) {
-  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(map) : "memory");
-}
 
 // streaming stores (the crops are consumed by the next kernel, never re-read by us)
 __device__ __forceinline__ void st_f4(float* p, float a, float b, float c, float d) {

@@ -23,14 +23,13 @@ namespace jnk {
 struct ImageRec {        // one per image when the set has several slabs (<= 32 bytes: jn_images_table_bytes)
   const uint8_t* base;   // first byte of this image's channel 0
   int32_t height, width; // pixels
-  int32_t map_index;     // tensor map of the slab this image lives in
+  int32_t slab;          // slab this image lives in
   int32_t plane0;        // index of this image's channel-0 plane inside its slab
 };
 
 struct GatherArgs {
   const uint8_t* base;        // single-slab sets: first byte of image 0
   const ImageRec* images;     // multi-slab sets: per-image records (device memory), else null
-  const CUtensorMap* maps;    // multi-slab sets, tensor engine: tensor maps (device memory)
   const int64_t* positions;   // [n_items, 2] (y, x) patch coordinates
   const int32_t* src_index;   // [n_items] image per item (negative = zero fill) or null = identity
   const int32_t* shifts;      // [n_images, 2] (ty, tx) integer translation of each image (zero fill) or null
@@ -51,7 +50,7 @@ struct Chunk {
   const uint8_t* src;  // first byte of the chunk's first row in the source image (null = zero fill)
   long long src_row_bytes;
   int item, channel, row0;  // tile-local first row
-  int map_index, plane, px, py;
+  int plane, px, py;  // plane = index of (image, channel) inside the slab: the tensor map's outer coordinate
   int sy, sx;  // translation of the source image: tile pixel (r, c) <- image pixel (py*P + r - sy, px*P + c - sx)
 };
 
@@ -64,7 +63,6 @@ __device__ __forceinline__ bool decode_chunk(const GatherArgs& a, int q, Chunk& 
   c.channel = rem / a.chunks_per_plane;
   c.row0 = (rem - c.channel * a.chunks_per_plane) * a.rows;
   c.src = nullptr;
-  c.map_index = 0;
   c.plane = 0;
   const int img = a.src_index ? a.src_index[c.item] : c.item;
   if (img < 0) return false;  // zero fill
@@ -74,7 +72,6 @@ __device__ __forceinline__ bool decode_chunk(const GatherArgs& a, int q, Chunk& 
   if (a.images) {
     const ImageRec r = a.images[img];
     base = r.base; h = r.height; w = r.width;
-    c.map_index = r.map_index;
     c.plane = r.plane0 + c.channel;
   } else {
     base = a.base + (long long)img * a.image_stride; h = a.height; w = a.width;
@@ -111,7 +108,7 @@ gather_copy_kernel(const __grid_constant__ GatherArgs a, const __grid_constant__
   if (lane == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
     fence_mbar_init();
-    if (kTensor && !a.maps) prefetch_tensormap(&map0);
+    if (kTensor) prefetch_tensormap(&map0);
   }
   for (int i = lane * 16; i < kZeroBytes; i += 32 * 16) *reinterpret_cast<uint4*>(zero + i) = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();  // zeros (generic proxy) -> visible to the bulk stores (async proxy)
@@ -133,8 +130,7 @@ gather_copy_kernel(const __grid_constant__ GatherArgs a, const __grid_constant__
         __syncwarp();
         if (kTensor) {
           if (lane == 0) {
-            const CUtensorMap* m = a.maps ? a.maps + c.map_index : &map0;
-            if (a.maps) fence_tensormap_acquire(m);
+            const CUtensorMap* m = &map0;
             if (a.shifts)  // 3-D map [W, H, planes]: arbitrary element offsets, out-of-image pixels arrive as zeros
               tensor_g2s_3d(stage, m, c.px * a.patch - c.sx, c.py * a.patch + c.row0 - c.sy, c.plane, &full[st]);
             else
@@ -237,7 +233,7 @@ gather_xform_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
       mbar_init(&empty[s], kConsumerWarps);
     }
     fence_mbar_init();
-    if (kTensor && !a.maps) prefetch_tensormap(&map0);
+    if (kTensor) prefetch_tensormap(&map0);
   }
   __syncthreads();
 
@@ -256,8 +252,7 @@ gather_xform_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
         __syncwarp();
         if (kTensor) {
           if (lane == 0) {
-            const CUtensorMap* m = a.maps ? a.maps + c.map_index : &map0;
-            if (a.maps) fence_tensormap_acquire(m);
+            const CUtensorMap* m = &map0;
             if (a.shifts)  // 3-D map [W, H, planes]: arbitrary element offsets, out-of-image pixels arrive as zeros
               tensor_g2s_3d(stage, m, c.px * a.patch - c.sx, c.py * a.patch + c.row0 - c.sy, c.plane, &full[st]);
             else
