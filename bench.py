@@ -153,8 +153,10 @@ class SupervisedWorkload:
 
         random.seed(step * 31 + self.rank)
         batch = {"image": self.images if images is None else images, "bboxes": self.bboxes, "class_id": self.class_ids}
+        self.stats = {}
         return generate_trajectories(batch, P, self.T, self.KMIN, self.KMAX, binomial_keypoints=self.BINOMIAL,
-                                     seeds=self.seeds(step), normalize=(self.src_dtype == "u8"), device=device)
+                                     seeds=self.seeds(step), normalize=(self.src_dtype == "u8"), device=device,
+                                     stats=self.stats)
 
     def gaze_steps(self, out):
         return out["masks"].sum()  # recorded glimpses (padded slots are not glimpses)
@@ -442,7 +444,9 @@ def main():
             hostres, d2h_bytes = wl.d2h(out)  # synchronising device -> host read of the step's result
             if zero_copy:  # tiles actually read over PCIe: recorded trajectory slots + detection patches
                 eunits += float(hostres["masks"].sum())
-                tiles = float(hostres["masks"].sum()) + out["patches_yolox"].shape[0]
+                # (detection patches that repeat a trajectory glimpse are copied inside HBM, not re-read from the host)
+                det_tiles = wl.stats.get("host_det_tiles", out["patches_yolox"].shape[0])
+                tiles = float(hostres["masks"].sum()) + float(det_tiles)
                 h2d += tiles * 3 * P * P * (1 if src == "u8" else 4)
             else:
                 eunits += float(wl.batch * (wl.T + 1))

@@ -46,6 +46,7 @@ typedef enum jn_dtype { JN_U8 = 0, JN_F32 = 1 } jn_dtype;
 #define JN_GATHER_NORMALIZE 1u /* uint8 source -> float32 output, value / 255 (ToTensor, dataset.py:240) */
 #define JN_GATHER_FOCUS 2u     /* output in YOLOX Focus space-to-depth layout [4*C, P/2, P/2] */
 #define JN_GATHER_SHIFT_ALIGNED 4u /* caller guarantees every x shift is a multiple of 16 bytes (TMA may serve it) */
+#define JN_GATHER_SKIP_NEGATIVE 8u /* items with a negative src_index are left untouched instead of zero-filled */
 
 /* jn_gather engine selection (JN_ENGINE_AUTO picks the fastest one the shapes allow) */
 typedef enum jn_engine {
@@ -222,6 +223,18 @@ int jn_traj_expand(const int32_t* start_yx /*[n,2]*/, const int32_t* seg_begin /
                    const int32_t* cols /*[n]*/, int n, int T, int64_t* positions,
                    int64_t* current_actions, int64_t* next_actions, int64_t* labels, float* masks,
                    int32_t* gather_src, int32_t* ep_len, int32_t* status, void* stream);
+
+/* Redirects gather queries to tiles that a previous gather already produced.  Trajectory records
+ * (traj_positions int64 [n*T, 2], traj_src int32 [n*T] = episode or -1, as written by
+ * jn_traj_expand) were gathered into a [n*T, C, P, P] buffer that is registered in the image set as a
+ * slab of n*T one-patch images starting at image index `slab_base`.  Query d (episode query_src[d],
+ * patch query_positions[d]) that matches a recorded slot of its episode becomes
+ * (image slab_base + e*T + t, patch (0, 0)); other queries are passed through.  Used for the
+ * detection patches of init_sample (simple_env.py:397-419), which mostly repeat trajectory glimpses:
+ * with host-resident images those tiles then stay off PCIe. */
+int jn_tile_lookup(const int64_t* traj_positions, const int32_t* traj_src, int T,
+                   const int64_t* query_positions, const int32_t* query_src, int n_queries,
+                   int slab_base, int64_t* out_positions, int32_t* out_src, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Host-side planner of supervised episodes (no GPU involved; all pointers are HOST memory).

@@ -15,7 +15,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 JN_OK, JN_ERR_INVALID, JN_ERR_CUDA, JN_ERR_UNSUPPORTED, JN_ERR_NO_DEVICE = range(5)
 JN_U8, JN_F32 = 0, 1
-GATHER_NORMALIZE, GATHER_FOCUS, GATHER_SHIFT_ALIGNED = 1, 2, 4
+GATHER_NORMALIZE, GATHER_FOCUS, GATHER_SHIFT_ALIGNED, GATHER_SKIP_NEGATIVE = 1, 2, 4, 8
 ENGINE_AUTO, ENGINE_TENSOR, ENGINE_BULK, ENGINE_LDG = 0, 1, 2, 3
 ENGINES = {"auto": ENGINE_AUTO, "tensor": ENGINE_TENSOR, "bulk": ENGINE_BULK, "ldg": ENGINE_LDG}
 RULE_ANY_PIXEL, RULE_AREA5 = 0, 1
@@ -53,6 +53,7 @@ SIGNATURES = {
     "jn_returns_rows": (c_int, [_P, c_int64, _P, c_int64, c_int, c_int, _P, _P]),
     "jn_traj_expand": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, c_int, c_int, _P, _P, _P, _P, _P, _P,
                                _P, _P, _P]),
+    "jn_tile_lookup": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, _P, _P, _P]),
     "jn_plan_create": (c_int, [POINTER(_P)]),
     "jn_plan_destroy": (None, [_P]),
     "jn_plan_error": (c_char_p, [_P]),
@@ -64,7 +65,7 @@ SIGNATURES = {
 # entry points that launch exactly one kernel of ours per successful call
 KERNEL_CALLS = frozenset({
     "jn_gather", "jn_patch_bitmaps", "jn_bitmap_unpack", "jn_split_boxes", "jn_local_boxes", "jn_env_reset",
-    "jn_env_step", "jn_env_props", "jn_env_rewards", "jn_returns", "jn_returns_rows", "jn_traj_expand",
+    "jn_env_step", "jn_env_props", "jn_env_rewards", "jn_tile_lookup", "jn_returns", "jn_returns_rows", "jn_traj_expand",
 })
 
 

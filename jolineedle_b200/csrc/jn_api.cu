@@ -358,6 +358,7 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
   a.status = status; a.n_items = n_items; a.n_images = set->n_images;
   a.channels = C; a.height = set->height; a.width = set->width; a.patch = P; a.elem = set->elem;
   a.box_w = set->box_w; a.kbox = set->kbox;
+  a.skip_negative = (flags & JN_GATHER_SKIP_NEGATIVE) ? 1 : 0;
 
   const bool plain_copy = !normalize && !focus;
   const bool out_aligned = reinterpret_cast<uintptr_t>(out) % 16 == 0 && out_item_stride_bytes % 16 == 0;
@@ -609,6 +610,21 @@ int jn_returns_rows(const float* rewards, int64_t rewards_row_stride, const uint
   JN_REQUIRE(rewards && logit_masks && returns, "jn_returns_rows: NULL pointer");
   jnk::returns_rows_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards, rewards_row_stride, logit_masks,
                                                                               masks_row_stride, T, n, returns);
+  JN_CUDA(cudaGetLastError());
+  return JN_OK;
+}
+
+int jn_tile_lookup(const int64_t* traj_positions, const int32_t* traj_src, int T, const int64_t* query_positions,
+                   const int32_t* query_src, int n_queries, int slab_base, int64_t* out_positions, int32_t* out_src,
+                   void* stream) {
+  JN_REQUIRE(T >= 1 && n_queries >= 0 && slab_base >= 0, "jn_tile_lookup: bad sizes");
+  if (n_queries == 0) return JN_OK;
+  JN_REQUIRE(traj_positions && traj_src && query_positions && query_src && out_positions && out_src,
+             "jn_tile_lookup: NULL pointer");
+  DeviceInfo dev;
+  if (int rc = current_device_info(dev)) return rc;
+  jnk::tile_lookup_kernel<<<grid_for(n_queries, 128, dev.sm_count * 8), 128, 0, (cudaStream_t)stream>>>(
+      traj_positions, traj_src, T, query_positions, query_src, n_queries, slab_base, out_positions, out_src);
   JN_CUDA(cudaGetLastError());
   return JN_OK;
 }

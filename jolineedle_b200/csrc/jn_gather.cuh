@@ -44,6 +44,7 @@ struct GatherArgs {
   int chunks_per_plane;         // patch / rows
   int total_chunks;             // n_items * channels * chunks_per_plane
   int box_w, kbox;              // tensor engine: patch = box_w * kbox
+  int skip_negative;            // negative src_index: 1 = leave the output tile untouched, 0 = zero-fill it
 };
 
 struct Chunk {
@@ -65,7 +66,7 @@ __device__ __forceinline__ bool decode_chunk(const GatherArgs& a, int q, Chunk& 
   c.src = nullptr;
   c.plane = 0;
   const int img = a.src_index ? a.src_index[c.item] : c.item;
-  if (img < 0) return false;  // zero fill
+  if (img < 0) return a.skip_negative != 0;  // zero fill, or skip when the caller asked for that
   const long long y = a.positions[2 * (long long)c.item], x = a.positions[2 * (long long)c.item + 1];
   const uint8_t* base;
   int h, w;
@@ -304,6 +305,7 @@ gather_rows_kernel(const GatherArgs a, const int out_f32, const int normalize, c
     int h = 0, w = 0;
     long long y = 0, x = 0;
     bool zero_row = img < 0;
+    if (zero_row && a.skip_negative) continue;
     if (!zero_row) {
       y = a.positions[2 * (long long)item]; x = a.positions[2 * (long long)item + 1];
       if (a.images) {
@@ -372,6 +374,7 @@ __global__ void gather_ldg_kernel(const GatherArgs a, const int out_f32, const i
     const int img = a.src_index ? a.src_index[item] : item;
     float fv = 0.f;
     uint8_t bv = 0;
+    if (img < 0 && a.skip_negative) continue;
     if (img >= 0) {
       const long long y = a.positions[2 * (long long)item], x = a.positions[2 * (long long)item + 1];
       const uint8_t* base;

@@ -47,6 +47,37 @@ __global__ void returns_rows_kernel(const float* __restrict__ rewards, long long
 }
 
 // ------------------------------------------------------------------------------------------
+// tile lookup: which detection patches were already gathered as trajectory glimpses?
+// ------------------------------------------------------------------------------------------
+// The detection patches of an image are its box patches plus one empty patch (simple_env.py:397-419)
+// and the trajectory visits exactly those box patches, so most detection tiles already sit in the
+// [n, T, C, P, P] trajectory buffer.  For query d (episode e = q_src[d], patch q_pos[d]) this finds a
+// recorded slot t of the same episode at the same patch and redirects the query to image
+// `slab_base + e*T + t`, patch (0, 0) -- the trajectory buffer registered as a slab of n*T one-patch
+// images.  When the images live in pinned host memory this keeps those tiles off PCIe.
+__global__ void tile_lookup_kernel(const int64_t* __restrict__ traj_pos, const int32_t* __restrict__ traj_src, int T,
+                                   const int64_t* __restrict__ q_pos, const int32_t* __restrict__ q_src, int n_queries,
+                                   int slab_base, int64_t* __restrict__ out_pos, int32_t* __restrict__ out_src) {
+  for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < n_queries; d += gridDim.x * blockDim.x) {
+    const int e = q_src[d];
+    long long y = q_pos[2 * (long long)d], x = q_pos[2 * (long long)d + 1];
+    int src = e;
+    if (e >= 0) {
+      for (int t = 0; t < T; ++t) {
+        const long long k = (long long)e * T + t;
+        if (traj_src[k] == e && traj_pos[2 * k] == y && traj_pos[2 * k + 1] == x) {
+          src = slab_base + (int)k;
+          y = 0; x = 0;
+          break;
+        }
+      }
+    }
+    out_pos[2 * (long long)d] = y; out_pos[2 * (long long)d + 1] = x;
+    out_src[d] = src;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // trajectory expansion (simple_env.py:481-664)
 // ------------------------------------------------------------------------------------------
 // One warp per episode.  The host planner supplies the key points in visiting order as

@@ -409,9 +409,8 @@ class NeedleSimpleEnv:
         reference's ``device`` argument is accepted and ignored when it says "cpu"."""
         plan = self.plan_sample(min_keypoints, max_keypoints, binomial_keypoints, position, visited_bbox_patches)
         batch = expand_plans([self], [plan], max_ep_len, image_set=self._ensure_set())
-        batch.pop("_ep_len")
-        batch.pop("_status")
-        sample = {k: (v[0] if k not in ("patches_yolox", "bboxes_yolox") else v) for k, v in batch.items()}
+        sample = {k: (v[0] if k not in ("patches_yolox", "bboxes_yolox") else v) for k, v in batch.items()
+                  if not k.startswith("_")}
         assert sample["patches"].shape[0] == max_ep_len
         return sample
 

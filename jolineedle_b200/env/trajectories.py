@@ -174,7 +174,7 @@ def _upload(array: np.ndarray, device) -> torch.Tensor:
 
 
 def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normalize: bool = False,
-                  engine: str = "auto") -> Dict[str, torch.Tensor]:
+                  engine: str = "auto", reuse_glimpses: bool = True) -> Dict[str, torch.Tensor]:
     """Packed plans -> the collated sample dict of the reference (keys ``patches``,
     ``current_actions``, ``next_actions``, ``positions``, ``masks``, ``labels``, ``local_bboxes``,
     ``patches_yolox``, ``bboxes_yolox``; plus ``_ep_len`` / ``_status`` for diagnostics)."""
@@ -248,10 +248,44 @@ def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normaliz
     # reuse it from batch to batch although the number of detection patches varies -- a fresh multi-GB
     # cudaMalloc costs tens of milliseconds; the result is a view of the buffer's head)
     quantum = max(n, 64)
-    det_cap = -(-max(n_det, 1) // quantum) * quantum
+    per_image = -(-max(n_det, 1) // quantum)
+    per_image = next((k for k in (1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128) if k >= per_image), per_image)
+    det_cap = per_image * quantum
     det_buf = torch.empty(image_set.out_shape(det_cap, False), dtype=torch.float32, device=dev)
-    out["patches_yolox"] = image_set.gather(d_det_pos, src_index=d_det_src, out=det_buf[:n_det], normalize=normalize,
-                                            engine=engine, status=status, tag="detection")
+    if image_set.host_mapped and reuse_glimpses and n_det > 0:
+        # Host-resident images: most detection patches were just gathered as trajectory glimpses, so take
+        # those from the [n*T, C, P, P] buffer in HBM instead of pulling them over PCIe a second time.  The
+        # buffer joins the image set as one more slab of n*T one-patch images.
+        traj_tiles = out["patches"].view((n * T,) + out["patches"].shape[2:])
+        if normalize:
+            # uint8 host images but float32 glimpses: two passes over the same output, each leaving the other's
+            # items untouched (skip_negative): normalising gather of the host tiles, plain copy of the reused ones
+            reuse_set = ImageSet(traj_tiles, P)
+            pos2 = torch.empty((n_det, 2), dtype=torch.long, device=dev)
+            src2 = torch.empty((n_det,), dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                _cabi.check(lib.jn_tile_lookup(out["positions"].data_ptr(), gather_src.data_ptr(), T,
+                                               d_det_pos.data_ptr(), d_det_src.data_ptr(), n_det, image_set.n_images,
+                                               pos2.data_ptr(), src2.data_ptr(), stream))
+            minus_one, n_img = torch.full_like(src2, -1), image_set.n_images
+            image_set.gather(pos2, src_index=torch.where(src2 < n_img, src2, minus_one), out=det_buf[:n_det],
+                             normalize=True, engine=engine, status=status, tag="detection", skip_negative=True)
+            reuse_set.gather(pos2, src_index=torch.where(src2 >= n_img, src2 - n_img, minus_one), out=det_buf[:n_det],
+                             engine=engine, status=status, tag="detection-reuse", skip_negative=True)
+        else:
+            joint = ImageSet(list(image_set._slabs) + [traj_tiles], P, device=dev)
+            pos2 = torch.empty((n_det, 2), dtype=torch.long, device=dev)
+            src2 = torch.empty((n_det,), dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                _cabi.check(lib.jn_tile_lookup(out["positions"].data_ptr(), gather_src.data_ptr(), T,
+                                               d_det_pos.data_ptr(), d_det_src.data_ptr(), n_det, image_set.n_images,
+                                               pos2.data_ptr(), src2.data_ptr(), stream))
+            joint.gather(pos2, src_index=src2, out=det_buf[:n_det], engine=engine, status=status, tag="detection")
+        out["patches_yolox"] = det_buf[:n_det]
+        out["_host_det_tiles"] = (src2 < image_set.n_images).sum()  # detection tiles that did cross PCIe
+    else:
+        out["patches_yolox"] = image_set.gather(d_det_pos, src_index=d_det_src, out=det_buf[:n_det],
+                                                normalize=normalize, engine=engine, status=status, tag="detection")
     det_boxes = torch.empty((n_det, n_max, 6), dtype=torch.float32, device=dev)
     if n_max > 0 and n_det > 0:
         with torch.cuda.device(dev):
@@ -312,6 +346,7 @@ def generate_trajectories(
     engine: str = "auto",
     planner: str = "auto",
     zero_copy: bool = True,
+    stats: Optional[dict] = None,
 ) -> Dict[str, torch.Tensor]:
     """Batched supervised trajectories (``SupervisedTrainer.generate_trajectories``,
     supervised.py:95-136): ``batch`` holds lists ``image`` ([C,H,W] tensors), ``bboxes`` (lists
@@ -331,6 +366,7 @@ def generate_trajectories(
     out = expand_packed(image_set, packed, max_seq_len, normalize, engine)
     class_id = np.array([int(c) for c in batch["class_id"]], dtype=np.int64)
     out["class_id"] = _upload(class_id, image_set.device)
-    out.pop("_ep_len")
-    out.pop("_status")
+    diagnostics = {k: out.pop(k) for k in [k for k in out if k.startswith("_")]}
+    if stats is not None:  # device scalars / tensors for benchmarks: untruncated lengths, tiles read from the host
+        stats.update({k[1:]: v for k, v in diagnostics.items()})
     return out

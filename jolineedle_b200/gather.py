@@ -115,6 +115,7 @@ class ImageSet:
         tag: str = "",
         shifts: Optional[torch.Tensor] = None,
         shifts_aligned: bool = False,
+        skip_negative: bool = False,
     ) -> torch.Tensor:
         """Tile ``positions[i] = (y, x)`` of image ``src_index[i]`` (default ``i``; negative =
         zeros) -> ``out[i]``.  ``out`` may be any tensor whose ``out[i]`` is contiguous (e.g. a
@@ -144,6 +145,8 @@ class ImageSet:
         flags = (_cabi.GATHER_NORMALIZE if normalize else 0) | (_cabi.GATHER_FOCUS if focus else 0)
         if shifts is not None and shifts_aligned:  # every x shift is a multiple of 16 bytes: TMA may serve it
             flags |= _cabi.GATHER_SHIFT_ALIGNED
+        if skip_negative:  # negative src_index: leave out[i] as it is (default: zero-fill it)
+            flags |= _cabi.GATHER_SKIP_NEGATIVE
         stride = out.stride(0) * out.element_size() if n > 1 else out[0].numel() * out.element_size() if n else 0
         timing = TIMING
         with torch.cuda.device(self.device):
