@@ -195,44 +195,25 @@ __device__ __forceinline__ void xform_chunk(const GatherArgs& a, const Chunk& c,
     const int q4 = P / 4;  // 4-pixel groups per row
     const int n = a.rows * q4;
     const long long plane = (long long)half * half;
-    // Each lane de-interleaves 4 pixels (2 even, 2 odd columns).  Lane pairs then swap halves so that the even
-    // lane of a pair owns 4 consecutive EVEN-column outputs and the odd lane 4 consecutive ODD-column outputs:
-    // one 16-byte store per lane instead of two 8-byte ones.  (Pairs never straddle a row when P/4 is even.)
-    const bool pair = (q4 & 1) == 0;
-    const int lane = tid & 31;
 #pragma unroll 2
-    for (int i0 = tid - lane; i0 < n; i0 += nthreads) {  // warp-uniform trip count: the shuffles see all lanes
-      const int i = i0 + lane;
-      const bool ok = i < n;
-      const int r = ok ? i / q4 : 0, g = ok ? i - r * q4 : 0;
+    for (int i = tid; i < n; i += nthreads) {
+      const int r = i / q4, g = i - r * q4;
       const int y = c.row0 + r;
-      float e0 = 0.f, o0 = 0.f, e1 = 0.f, o1 = 0.f;
-      if (ok && !zero) {
-        if (kMode == kF32Focus) {
-          const float4 v = reinterpret_cast<const float4*>(stage)[i];
-          e0 = v.x; o0 = v.y; e1 = v.z; o1 = v.w;
-        } else {
-          const uint32_t u = reinterpret_cast<const uint32_t*>(stage)[i];
-          e0 = u8_to_unit((float)(u & 0xFF)); o0 = u8_to_unit((float)((u >> 8) & 0xFF));
-          e1 = u8_to_unit((float)((u >> 16) & 0xFF)); o1 = u8_to_unit((float)(u >> 24));
-        }
+      float e0, o0, e1, o1;
+      if (kMode == kF32Focus) {
+        const float4 v = zero ? make_float4(0.f, 0.f, 0.f, 0.f)
+                              : reinterpret_cast<const float4*>(stage)[i];
+        e0 = v.x; o0 = v.y; e1 = v.z; o1 = v.w;
+      } else {
+        const uint32_t u = zero ? 0u : reinterpret_cast<const uint32_t*>(stage)[i];
+        e0 = u8_to_unit((float)(u & 0xFF)); o0 = u8_to_unit((float)((u >> 8) & 0xFF));
+        e1 = u8_to_unit((float)((u >> 16) & 0xFF)); o1 = u8_to_unit((float)(u >> 24));
       }
       const int dy = y & 1;
       float* even = out_item + ((long long)(dy * a.channels + c.channel)) * plane + (long long)(y >> 1) * half + 2 * g;
       float* odd = even + 2ll * a.channels * plane;
-      if (pair) {
-        const bool odd_lane = lane & 1;
-        // send the half the partner stores: the even lane gives away its odd columns and vice versa
-        const float r0 = __shfl_xor_sync(0xffffffffu, odd_lane ? e0 : o0, 1);
-        const float r1 = __shfl_xor_sync(0xffffffffu, odd_lane ? e1 : o1, 1);
-        if (ok) {
-          if (!odd_lane) st_f4(even, e0, e1, r0, r1);   // columns 8k, 8k+2 | 8k+4, 8k+6
-          else st_f4(odd - 2, r0, r1, o0, o1);          // columns 8k+1, 8k+3 | 8k+5, 8k+7 (group g-1 starts 2 floats earlier)
-        }
-      } else if (ok) {
-        st_f2(even, e0, e1);
-        st_f2(odd, o0, o1);
-      }
+      st_f2(even, e0, e1);
+      st_f2(odd, o0, o1);
     }
   }
 }
