@@ -51,11 +51,8 @@ class NeedleGeneralEnv:
         assert images.shape[0] == bboxes.shape[0]
         assert len(images.shape) == 4
         assert n_glimps_levels > 0
-        if n_glimps_levels != 1:
-            raise NotImplementedError(
-                "n_glimps_levels > 1 (the zoomed-out glimpse pyramid, general_env.py:84-115) is not built; "
-                "every caller in the reference pins it to 1 (reinforce.py:58)"
-            )
+        if n_glimps_levels != 1 and (translate is not None or images.dtype != torch.float32):
+            raise NotImplementedError("the glimpse pyramid (n_glimps_levels > 1) needs float32 images and no translate")
         if device is not None and not images.is_cuda:
             images = images.to(device, non_blocking=True)
         _cabi.require_cuda(images, "images")
@@ -79,9 +76,14 @@ class NeedleGeneralEnv:
             self._shifts_aligned = bool(((t[:, 0].to(torch.int64) * elem) % 16 == 0).all()) if not t.is_cuda else False
             self._shifts = t.to(torch.int32).flip(1).contiguous().to(self.device)
 
-        self._set = ImageSet(images, patch_size)
-        # [B, G=1, C, H, W] view of the caller's tensor (callers read env.images[0, 0])
-        self.images = self._set._slabs[0].unsqueeze(1)
+        if n_glimps_levels == 1:
+            self._set = ImageSet(images, patch_size)
+            # [B, G=1, C, H, W] view of the caller's tensor (callers read env.images[0, 0]); the reflect-pad +
+            # resize the reference computes and throws away at one level (general_env.py:95-111) is not done
+            self.images = self._set._slabs[0].unsqueeze(1)
+        else:
+            self.images = self.init_glimps_images(images)  # [B, G, C, H, W]
+            self._set = ImageSet(self.images.view((-1,) + tuple(self.images.shape[2:])), patch_size)
         self.bboxes = bboxes
         self._boxes_dev = bboxes.to(device=self.device, dtype=torch.int64).contiguous()
         self._words = (self.n_vertical_patches * self.n_horizontal_patches + 31) // 32
@@ -100,11 +102,32 @@ class NeedleGeneralEnv:
 
         self._history: Optional[Tensor] = None
         if history:
+            # the glimpse axis doubles as the time axis of the history, as in the trainer's concat (reinforce.py:176)
             self._history = torch.empty(
-                (self.batch_size, max_ep_len + 1) + self._set.out_shape(1, focus)[1:],
+                (self.batch_size, (max_ep_len + 1) * n_glimps_levels) + self._set.out_shape(1, focus)[1:],
                 dtype=self._set.out_dtype(normalize), device=self.device)
+        if n_glimps_levels > 1:
+            levels = n_glimps_levels
+            ids = torch.arange(self.batch_size * levels, dtype=torch.int32, device=self.device)
+            self._level_src = [ids[l::levels].contiguous() for l in range(levels)]  # image b*G + l of level l
         self._t = 0
         self.init_env_variables()
+
+    @torch.no_grad()
+    def init_glimps_images(self, images: Tensor) -> Tensor:
+        """Stack of progressively zoomed-out copies of the images (general_env.py:84-115): level 0 is the input,
+        level k+1 = level k reflect-padded by one patch on every side and resized (antialiased bilinear) back to
+        H x W.  Built once per env with the same torchvision calls as the reference, on the GPU (library ops, not
+        on the step path); the per-step crops then come from all levels through the K1 gather.  The GPU resize
+        agrees with the reference's CPU resize to float rounding (~1e-7), not bit for bit."""
+        import torchvision.transforms.functional as TF
+
+        levels, current = [], images
+        for _ in range(self.n_glimps_levels):
+            levels.append(current)
+            current = TF.pad(current, padding=[self.patch_size] * 4, padding_mode="reflect")
+            current = TF.resize(current, size=[self.height, self.width], antialias=True)
+        return torch.stack(levels, dim=1).contiguous()
 
     # ------------------------------------------------------------------------------------
     def _stream(self):
@@ -148,6 +171,8 @@ class NeedleGeneralEnv:
 
     # ------------------------------------------------------------------------------------
     def _gather(self) -> Tensor:
+        if self.n_glimps_levels > 1:
+            return self._gather_levels()
         out = None
         if self._history is not None:
             out = self._history[:, self._t]
@@ -156,15 +181,29 @@ class NeedleGeneralEnv:
                                    shifts_aligned=self._shifts_aligned)
         return patches.unsqueeze(1)  # [B, G=1, C, P, P]
 
+    def _gather_levels(self) -> Tensor:
+        """``[B, G, C, P, P]``: the same patch out of every glimpse level (one gather per level; level l of
+        episode b is image b*G + l of the stacked set)."""
+        g = self.n_glimps_levels
+        if self._history is not None:
+            out = self._history[:, self._t * g:(self._t + 1) * g]
+        else:
+            out = torch.empty((self.batch_size, g) + self._set.out_shape(1, self._focus)[1:],
+                              dtype=self._set.out_dtype(self._normalize), device=self.device)
+        for level in range(g):
+            self._set.gather(self.positions, src_index=self._level_src[level], out=out[:, level], focus=self._focus,
+                             engine=self._engine, status=self._status, tag="step")
+        return out
+
     @property
     def patches(self) -> Tensor:  # general_env.py:285-306
         return self._gather()
 
     def patch_history(self, upto: Optional[int] = None) -> Tensor:
-        """``[B, t+1, C, P, P]`` view of every crop produced so far (needs ``history=True``)."""
+        """``[B, (t+1)*G, C, P, P]`` view of every crop produced so far (needs ``history=True``)."""
         if self._history is None:
             raise RuntimeError("construct the env with history=True to keep the crop history")
-        return self._history[:, : (self._t if upto is None else upto) + 1]
+        return self._history[:, : ((self._t if upto is None else upto) + 1) * self.n_glimps_levels]
 
     def reset(self, positions: Optional[Tensor] = None) -> Tuple[Tensor, dict]:  # general_env.py:144-170
         self.init_env_variables()
@@ -316,7 +355,10 @@ class NeedleGeneralEnv:
         r_all, c_all = torch.cat(rows_ids), torch.cat(cols_ids)
         positions = torch.stack((r_all, c_all), dim=1).to(self.device)
         src = torch.tensor(img_ids, dtype=torch.int32, device=self.device)
-        patches = self._set.gather(positions, src_index=src, engine=self._engine, status=self._status)
+        # glimpse level 0 of image i is image i*G of the stacked set (general_env.py:533-539)
+        patches = self._set.gather(positions, src_index=src * self.n_glimps_levels, normalize=self._normalize,
+                                   engine=self._engine, status=self._status, shifts=self._shifts,
+                                   shifts_aligned=self._shifts_aligned)
         src_l = src.long()
         boxes = local[src_l, positions[:, 0], positions[:, 1]]  # [n, N, 4]
         boxes = torch.nn.functional.pad(boxes, (1, 0))  # class id 0 in front
