@@ -329,6 +329,7 @@ def main():
                     help="distinct pinned host images per rank in the e2e arm (default: all of them up to 2 ranks, "
                          "64 beyond, to bound page-locked host memory at 8 ranks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi (A/B of the sampler's own cost)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -358,7 +359,9 @@ def main():
     src = args.src if args.workload == "supervised" else "u8"  # RL workloads keep uint8-resident images
     wl = cls(args.batch or default_batch, rank, device, src)
     # nvidia-smi is started here, seconds before the timed region: its NVML start-up stalls CUDA calls
-    clocks = ClockSampler(local_rank).__enter__()
+    clocks = ClockSampler(local_rank)
+    if not args.no_clocks:
+        clocks.__enter__()
     wl.to_device()
     peaks = {}
     try:
@@ -415,8 +418,20 @@ def main():
         dur.append(e0.elapsed_time(e1))
         byts.append(wl.gather_bytes(n_items, v, tag))
     achieved = (sum(byts) / len(byts)) / (sum(dur) / len(dur) / 1e3) / 1e9 if dur else 0.0
+    # DRAM traffic per launch of that kernel from the committed `ncu --set full` capture of this workload at its
+    # default batch (profiles/r01/ncu_summary.json, produced by tools/gpu_ci.sh ncu); null when there is none
+    traffic, traffic_src = None, None
+    try:
+        summary = json.load(open(os.path.join(ROOT, "profiles", "r01", "ncu_summary.json")))
+        prefix = "gather_copy_kernel" if args.workload == "supervised" and src == "f32" else None
+        if prefix and wl.batch == default_batch:
+            rec = next(v[0] for k_, v in summary["supervised"].items() if k_.startswith(prefix))
+            traffic, traffic_src = int(rec["dram_traffic_bytes"]), "profiles/r01/ncu_summary.json (ncu --set full)"
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json)",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": f"{peak_kind} (MEASURED_PEAKS.json)",
                 "kernel": "gather (K1), tag=" + main_tag, "launches_timed": len(dur),
                 "avg_launch_ms": round(sum(dur) / len(dur), 4) if dur else None,
                 "algorithmic_bytes_per_launch": int(sum(byts) / len(byts)) if byts else 0}
@@ -469,13 +484,14 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
         sample = args.cpu_sample or {"supervised": 32, "reinforce": 8, "aerial": 2}[args.workload]
-        reps = 8 if args.workload == "supervised" else 3
+        budget_s = 12.0  # bounded sample: ~10-30 s of CPU work
         wl.cpu_sample(sample, 0)
-        u_sum, t_sum = 0.0, 0.0
-        for r in range(reps):
-            u, dt = wl.cpu_sample(sample, 100 + r)
+        u_sum, t_sum, reps = 0.0, 0.0, 0
+        while t_sum < budget_s and reps < 400:
+            u, dt = wl.cpu_sample(sample, 100 + reps)
             u_sum += u
             t_sum += dt
+            reps += 1
         cpu = {"value": u_sum / t_sum, "unit": "gaze-steps/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{reps} x {sample} episodes of the same workload through the oracle port of the reference "
                          f"CPU env ({t_sum:.1f} s of CPU work)"}

@@ -180,7 +180,7 @@ GatherTune gather_tune(int patch, int elem, bool plain_copy, bool focus, int eng
   // with several CTAs per SM beat one deep ring: 2-3 stages, lookahead 1, 2-4 CTAs/SM.
   const int bucket = patch <= 128 ? 0 : patch <= 256 ? 1 : patch < 1024 ? 2 : 3;
   static const int copy[4][4] = {{2, 1, 32768, 3}, {3, 1, 32768, 2}, {3, 1, 32768, 2}, {2, 1, 16384, 3}};
-  static const int norm_plain[4][3] = {{2, 16384, 3}, {3, 8192, 2}, {3, 16384, 1}, {2, 8192, 2}};
+  static const int norm_plain[4][3] = {{2, 16384, 3}, {3, 8192, 2}, {4, 32768, 1}, {2, 8192, 2}};
   static const int norm_focus[4][3] = {{2, 16384, 4}, {3, 16384, 2}, {3, 16384, 2}, {2, 16384, 2}};
   static const int f32_focus[4][3] = {{2, 16384, 3}, {3, 16384, 2}, {3, 16384, 2}, {3, 32768, 1}};
   t.copy_stages = copy[bucket][0]; t.copy_ahead = copy[bucket][1]; t.copy_chunk = copy[bucket][2];
@@ -374,7 +374,13 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
   if (engine == JN_ENGINE_AUTO) {
     if (!tma_mode || !out_aligned || !set->bulk_ok) engine = JN_ENGINE_LDG;
     else if (shifts) engine = shift_tensor_ok ? JN_ENGINE_TENSOR : JN_ENGINE_LDG;
-    else engine = (set->tensor_ok && set->n_slabs == 1) ? JN_ENGINE_TENSOR : JN_ENGINE_BULK;
+    else {
+      // uint8 -> fp32 plain tiles of 256 < P < 1024: per-row bulk copies into 4 x 28 KB stages measured 3-4 %
+      // faster than tensor tiles (profiles/r01/tune_sweep_summary.txt); everywhere else the engines tie or the
+      // tensor tiles win
+      const bool prefer_bulk = normalize && !focus && P > 256 && P < 1024;
+      engine = (set->tensor_ok && set->n_slabs == 1 && !prefer_bulk) ? JN_ENGINE_TENSOR : JN_ENGINE_BULK;
+    }
   }
   if (shifts && engine == JN_ENGINE_TENSOR)
     JN_REQUIRE(shift_tensor_ok, "translated gathers on the tensor engine need one slab, patch_size <= 256 and "
@@ -435,9 +441,9 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
     return fail(JN_ERR_INVALID, "JN_GATHER_TUNE: no copy kernel with %d stages / lookahead %d", tune.copy_stages,
                 tune.copy_ahead);
   }
-  const size_t smem = tune.xform_stages * chunk_bytes + 2 * tune.xform_stages * sizeof(uint64_t);
   const int threads = (kXformWarps + 1) * 32;
   const bool tensor = engine == JN_ENGINE_TENSOR;
+  const size_t smem = tune.xform_stages * chunk_bytes + 2 * tune.xform_stages * sizeof(uint64_t);
 #define JN_XFORM_S(mode, S)                                                                                        \
   if (tune.xform_stages == S)                                                                                      \
     return tensor ? launch_persistent(jnk::gather_xform_kernel<mode, S, kXformWarps, true>, a, map, threads, smem, dev, \

@@ -6,9 +6,12 @@
 //   xform  kernel: uint8 -> float32 normalisation and / or the Focus space-to-depth layout.
 //                  Warp 0 is the TMA producer, the other warps read the staged tile from
 //                  shared memory, convert, and write coalesced vector stores.
-//   ldg    kernel: element-wise fallback for shapes the TMA engines cannot address
-//                  (rows or patches that are not 16-byte multiples); also the in-GPU
-//                  cross-check of the other two in the tests.
+//   rows   kernel: plain loads, one warp per tile row: what the TMA unit cannot address --
+//                  source rows that do not start on a 16-byte boundary (arbitrary integer
+//                  translation), lists of images combined with a translation.
+//   ldg    kernel: element-wise last resort (patch sizes that are not multiples of 4, outputs
+//                  that are not 16-byte aligned); with the rows kernel it is the "ldg" engine
+//                  and the in-GPU cross-check of the TMA engines in the tests.
 //
 // Work decomposition: a *chunk* is `rows` consecutive rows of one channel of one tile
 // (rows * P * elem bytes, contiguous in the plain output).  Chunks are dealt round-robin to
@@ -132,7 +135,7 @@ gather_copy_kernel(const __grid_constant__ GatherArgs a, const __grid_constant__
         if (kTensor) {
           if (lane == 0) {
             const CUtensorMap* m = &map0;
-            if (a.shifts)  // 3-D map [W, H, planes]: arbitrary element offsets, out-of-image pixels arrive as zeros
+            if (a.shifts)  // 3-D map [W, H, planes]: x offsets in 16-byte steps, any y; out-of-image pixels arrive as zeros
               tensor_g2s_3d(stage, m, c.px * a.patch - c.sx, c.py * a.patch + c.row0 - c.sy, c.plane, &full[st]);
             else
               tensor_g2s_4d(stage, m, 0, c.px * a.kbox, c.py * a.patch + c.row0, c.plane, &full[st]);
@@ -254,7 +257,7 @@ gather_xform_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
         if (kTensor) {
           if (lane == 0) {
             const CUtensorMap* m = &map0;
-            if (a.shifts)  // 3-D map [W, H, planes]: arbitrary element offsets, out-of-image pixels arrive as zeros
+            if (a.shifts)  // 3-D map [W, H, planes]: x offsets in 16-byte steps, any y; out-of-image pixels arrive as zeros
               tensor_g2s_3d(stage, m, c.px * a.patch - c.sx, c.py * a.patch + c.row0 - c.sy, c.plane, &full[st]);
             else
               tensor_g2s_4d(stage, m, 0, c.px * a.kbox, c.py * a.patch + c.row0, c.plane, &full[st]);

@@ -213,7 +213,9 @@ class NeedleGeneralEnv:
             # host RNG in the reference's order: rows first, then columns, CPU default generator
             ys = torch.randint(low=0, high=self.n_vertical_patches, size=(self.batch_size,))
             xs = torch.randint(low=0, high=self.n_horizontal_patches, size=(self.batch_size,))
-            self.positions = torch.stack((ys, xs), dim=1).to(self.device, non_blocking=True)
+            staged = torch.empty((self.batch_size, 2), dtype=torch.long, pin_memory=True)
+            torch.stack((ys, xs), dim=1, out=staged)  # pinned staging: the upload does not wait for the stream
+            self.positions = staged.to(self.device, non_blocking=True)
         assert tuple(self.positions.shape) == (self.batch_size, 2)
         with torch.cuda.device(self.device):
             _cabi.check(self._lib.jn_env_reset(

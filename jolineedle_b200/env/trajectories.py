@@ -96,6 +96,7 @@ class _NativePlan:
 
 
 _native_plan: Optional[_NativePlan] = None
+_det_capacity: Dict[tuple, int] = {}  # high-water mark of detection tiles per batch (see expand_packed)
 
 
 def native_supported(rows: np.ndarray, cols: np.ndarray, exact_boxes: bool, seeds) -> bool:
@@ -244,13 +245,15 @@ def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normaliz
                      out=out["patches"].view((n * T,) + out["patches"].shape[2:]), normalize=normalize,
                      engine=engine, status=status, tag="trajectory")
     # detection patches: every box patch + one random empty patch per image (simple_env.py:397-441)
-    # (the buffer is sized to a whole number of tiles per image so that torch's caching allocator can
-    # reuse it from batch to batch although the number of detection patches varies -- a fresh multi-GB
-    # cudaMalloc costs tens of milliseconds; the result is a view of the buffer's head)
-    quantum = max(n, 64)
-    per_image = -(-max(n_det, 1) // quantum)
-    per_image = next((k for k in (1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128) if k >= per_image), per_image)
-    det_cap = per_image * quantum
+    # (the number of detection patches varies from batch to batch, and a buffer of a new size is a fresh
+    # multi-GB cudaMalloc -- tens of milliseconds -- for torch's caching allocator.  So the capacity only
+    # ever grows, with 1/8 headroom, per (device, tile shape, batch size): after the first batches every request has the
+    # same size and is served from the cache; the result is a view of the buffer's head)
+    key = (dev, image_set.channels, P, n)
+    need = max(n_det, 1)
+    det_cap = _det_capacity.get(key, 0)
+    if need > det_cap:
+        det_cap = _det_capacity[key] = -(-(need + need // 8) // 64) * 64
     det_buf = torch.empty(image_set.out_shape(det_cap, False), dtype=torch.float32, device=dev)
     if image_set.host_mapped and reuse_glimpses and n_det > 0:
         # Host-resident images: most detection patches were just gathered as trajectory glimpses, so take
