@@ -199,7 +199,7 @@ class SupervisedWorkload:
 class ReinforceWorkload:
     name = ("cfg3 reinforce: LARD-shaped 2240x2688 (padded), patch 448, max-seq-len 20, enable-stop, seeded random "
             "actions, uint8-resident images normalised on gather")
-    T, PATCH, GRID = 20, P, (GH, GW)
+    T, PATCH, GRID, TRANSLATE = 20, P, (GH, GW), False
 
     def __init__(self, batch, rank, device, src_dtype):
         self.batch, self.rank, self.device, self.src_dtype = batch, rank, device, src_dtype
@@ -210,6 +210,21 @@ class ReinforceWorkload:
         boxes = np.zeros((batch, nmax, 4), dtype=np.int64)  # zero-padded rows like padded_collate_fn
         for i, r in enumerate(raw):
             boxes[i, :len(r)] = r
+        self.translate = None
+        if self.TRANSLATE:
+            # augment-translate (dataset.py:157-226): per image an integer (tx, ty) inside the margins that keep
+            # every box in the image, capped at a third of the image; boxes move with it, pixels are shifted by
+            # the gather itself (zero fill), the translated image is never materialised
+            shifts = np.zeros((batch, 2), dtype=np.int64)
+            for i, r in enumerate(raw):
+                a = np.array(r)
+                lo_x, lo_y = min(self.w // 3, a[:, 0].min()), min(self.h // 3, a[:, 1].min())
+                hi_x, hi_y = min(self.w // 3, self.w - a[:, 2].max()), min(self.h // 3, self.h - a[:, 3].max())
+                tx = 0 if lo_x == 0 and hi_x == 0 else int(rng.integers(-lo_x, hi_x))
+                ty = 0 if lo_y == 0 and hi_y == 0 else int(rng.integers(-lo_y, hi_y))
+                shifts[i] = (tx, ty)
+                boxes[i, :len(r)] += (tx, ty, tx, ty)
+            self.translate = torch.from_numpy(shifts)
         self.boxes = torch.from_numpy(boxes)
 
     def to_device(self):
@@ -222,7 +237,8 @@ class ReinforceWorkload:
 
         imgs = self.images if images is None else images
         env = NeedleGeneralEnv(imgs, self.boxes, self.PATCH, self.T, 1, stop_enabled=True,
-                               normalize=(self.src_dtype == "u8"), history=True, device=device)
+                               normalize=(self.src_dtype == "u8"), history=True, device=device,
+                               translate=self.translate)
         torch.manual_seed(step * 31 + self.rank)
         self.gen.manual_seed(step * 31 + self.rank)
         b = self.batch
@@ -275,8 +291,9 @@ class ReinforceWorkload:
 
 class AerialWorkload(ReinforceWorkload):
     name = ("cfg4 aerial: 8192x8192 synthetic images, patch 256 (32x32 grid, 1024-bit bitmaps), max-seq-len 32, "
-            "enable-stop, seeded random actions, uint8-resident images normalised on gather")
-    T, PATCH, GRID = 32, 256, (32, 32)
+            "enable-stop, augment-translate folded into the gather, seeded random actions, uint8-resident images "
+            "normalised on gather")
+    T, PATCH, GRID, TRANSLATE = 32, 256, (32, 32), True
 
 
 WORKLOADS = {"supervised": (SupervisedWorkload, 256), "reinforce": (ReinforceWorkload, 1024),

@@ -11,7 +11,8 @@ from typing import Optional
 import torch
 
 _LIB_NAME = "libjolineedle_b200.so"
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+# JN_LIB_PATH: development override (A/B of two builds under the same harness)
+_LIB_PATH = os.environ.get("JN_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 JN_OK, JN_ERR_INVALID, JN_ERR_CUDA, JN_ERR_UNSUPPORTED, JN_ERR_NO_DEVICE = range(5)
 JN_U8, JN_F32 = 0, 1

@@ -78,6 +78,27 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+// Work counters of the xform kernel: {next unclaimed chunk, CTAs done} pairs that are zero between
+// launches (the kernel cleans up after itself).  Launches rotate through a pool so that gathers running
+// concurrently on different streams do not share a pair.  Allocated once per device.
+int* next_work_counter(int device) {
+  constexpr int kSlots = 1024;
+  struct Pool { int device; int* base; unsigned seq; };
+  static std::mutex mu;
+  static std::vector<Pool> pools;
+  std::lock_guard<std::mutex> lock(mu);
+  for (auto& p : pools)
+    if (p.device == device) return p.base + 2 * (p.seq++ % kSlots);
+  int* base = nullptr;
+  if (cudaMalloc(&base, kSlots * 2 * sizeof(int)) != cudaSuccess ||
+      cudaMemset(base, 0, kSlots * 2 * sizeof(int)) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  pools.push_back({device, base, 1u});
+  return base;
+}
+
 inline int grid_for(long long work_items, int per_block, int cap) {
   long long g = (work_items + per_block - 1) / per_block;
   if (g < 1) g = 1;
@@ -156,6 +177,26 @@ int encode_slab_map(CUtensorMap* map, const void* ptr, int elem, int n_planes, i
   return JN_OK;
 }
 
+// Translated gathers with arbitrary x offsets: 3-D view [W*elem/8] x [H] x [planes] of 8-byte elements,
+// box = [pitch/8] x [rows] x 1 with pitch = patch*elem + 16: the kernel asks for the 16-byte aligned
+// superset of every tile row; bytes outside the image arrive as zeros (rows are multiples of 8 bytes,
+// so the zero fill is exact at pixel granularity).
+int encode_shift_map(CUtensorMap* map, const void* ptr, int elem, int n_planes, int height, int width, int pitch,
+                     int rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(JN_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t row_bytes = (cuuint64_t)width * elem;
+  cuuint64_t dims[3] = {row_bytes / 8, (cuuint64_t)height, (cuuint64_t)n_planes};
+  cuuint64_t strides[2] = {row_bytes, row_bytes * height};
+  cuuint32_t box[3] = {(cuuint32_t)(pitch / 8), (cuuint32_t)rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(JN_ERR_CUDA, "cuTensorMapEncodeTiled (translated) failed with CUresult %d", (int)r);
+  return JN_OK;
+}
+
 }  // namespace
 
 namespace {
@@ -180,9 +221,11 @@ GatherTune gather_tune(int patch, int elem, bool plain_copy, bool focus, int eng
   // with several CTAs per SM beat one deep ring: 2-3 stages, lookahead 1, 2-4 CTAs/SM.
   const int bucket = patch <= 128 ? 0 : patch <= 256 ? 1 : patch < 1024 ? 2 : 3;
   static const int copy[4][4] = {{2, 1, 32768, 3}, {3, 1, 32768, 2}, {3, 1, 32768, 2}, {2, 1, 16384, 3}};
-  static const int norm_plain[4][3] = {{2, 16384, 3}, {3, 8192, 2}, {4, 32768, 1}, {2, 8192, 2}};
-  static const int norm_focus[4][3] = {{2, 16384, 4}, {3, 16384, 2}, {3, 16384, 2}, {2, 16384, 2}};
-  static const int f32_focus[4][3] = {{2, 16384, 3}, {3, 16384, 2}, {3, 16384, 2}, {3, 32768, 1}};
+  // xform kernel (dynamic chunk claiming, profiles/r01/tune_xform_v2_summary.txt): {stages, chunk bytes, CTAs/SM};
+  // the sweep is flat within 2-3 % around these
+  static const int norm_plain[4][3] = {{3, 4096, 3}, {3, 8192, 2}, {3, 16384, 1}, {4, 8192, 1}};
+  static const int norm_focus[4][3] = {{3, 4096, 3}, {3, 8192, 2}, {3, 16384, 1}, {4, 8192, 1}};
+  static const int f32_focus[4][3] = {{4, 4096, 4}, {3, 16384, 2}, {6, 16384, 1}, {3, 32768, 1}};
   t.copy_stages = copy[bucket][0]; t.copy_ahead = copy[bucket][1]; t.copy_chunk = copy[bucket][2];
   t.copy_ctas = copy[bucket][3];
   const int(*x)[3] = elem == 4 ? f32_focus : (focus ? norm_focus : norm_plain);
@@ -202,9 +245,9 @@ GatherTune gather_tune(int patch, int elem, bool plain_copy, bool focus, int eng
   return t;
 }
 
-template <typename Kernel>
+template <typename Kernel, typename... Extra>
 int launch_persistent(Kernel kernel, const jnk::GatherArgs& a, const CUtensorMap& map, int threads, size_t smem,
-                      const DeviceInfo& dev, cudaStream_t stream, int ctas_cap = 0) {
+                      const DeviceInfo& dev, cudaStream_t stream, int ctas_cap, Extra... extra) {
   JN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   JN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
@@ -212,7 +255,7 @@ int launch_persistent(Kernel kernel, const jnk::GatherArgs& a, const CUtensorMap
   if (ctas_cap > 0 && per_sm > ctas_cap) per_sm = ctas_cap;
   long long grid = (long long)dev.sm_count * per_sm;
   if (grid > a.total_chunks) grid = a.total_chunks;
-  kernel<<<(int)grid, threads, smem, stream>>>(a, map);
+  kernel<<<(int)grid, threads, smem, stream>>>(a, map, extra...);
   JN_CUDA(cudaGetLastError());
   return JN_OK;
 }
@@ -236,8 +279,11 @@ int jn_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 // Host-only self test of the two pieces of arithmetic shared with the device code: the
 // direction table and the uint8 -> [0,1] normalisation.  `unit_out` receives the 256 values.
 int jn_selftest_host(float* unit_out /*HOST [256]*/, int* direction_out /*HOST [9], index (sy+1)*3+(sx+1)*/) {
-  if (unit_out)
-    for (int i = 0; i < 256; ++i) unit_out[i] = jnk::u8_to_unit((float)i);
+  for (int i = 0; i < 256; ++i) {
+    const float a = jnk::u8_to_unit((float)i), b = jnk::unit_from_scaled((float)i / 256.0f);
+    if (a != b) return fail(JN_ERR_INVALID, "normalisation formulas disagree for %d: %.9g vs %.9g", i, a, b);
+    if (unit_out) unit_out[i] = b;
+  }
   if (direction_out)
     for (int sy = -1; sy <= 1; ++sy)
       for (int sx = -1; sx <= 1; ++sx) direction_out[(sy + 1) * 3 + (sx + 1)] = jnk::direction_code(sy * 3, sx * 5);
@@ -363,28 +409,34 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
   const bool plain_copy = !normalize && !focus;
   const bool out_aligned = reinterpret_cast<uintptr_t>(out) % 16 == 0 && out_item_stride_bytes % 16 == 0;
   // u8 -> u8 Focus has no TMA kernel (nobody asks for it); it runs on the LDG engine.
-  const bool tma_mode = plain_copy || normalize || (focus && set->dtype == JN_F32);
-  // Translated sources need arbitrary element offsets and zero fill outside the image: that is the
-  // 3-D tensor map with one box per row block (patch <= 256 elements, single slab); anything else
-  // goes to the plain-load engine.
-  // The TMA unit traps (illegal instruction) on inner coordinates that are not 16-byte multiples, so it only
-  // serves translations the caller vouches for (JN_GATHER_SHIFT_ALIGNED: every tx * elem % 16 == 0).
-  const bool shift_tensor_ok = set->tensor_ok && set->n_slabs == 1 && set->kbox == 1 &&
-                               (flags & JN_GATHER_SHIFT_ALIGNED) != 0;
+  // (the xform kernel divides by patch / 4 with a 32-bit multiply-high: patches of at least 8 pixels)
+  const bool tma_mode = plain_copy || (P >= 8 && (normalize || (focus && set->dtype == JN_F32)));
+  // Translated sources (zero fill outside the image), one slab:
+  //  * plain same-dtype copies whose x shifts the caller vouches for (JN_GATHER_SHIFT_ALIGNED: every
+  //    tx * elem % 16 == 0) stay pure DMA: copy kernel, element-typed 3-D map, patch <= 256;
+  //  * everything else that converts or re-lays out (and float32 plain copies) goes through the xform
+  //    kernel's superset loads: any x offset (the TMA unit itself traps on inner coordinates that are not
+  //    16-byte multiples), rows of up to 2032 bytes;
+  //  * the rest (lists of images, uint8 -> uint8, wider rows) is served by the plain-load engine.
+  const bool shift_copy_ok = plain_copy && set->tensor_ok && set->n_slabs == 1 && set->kbox == 1 &&
+                             (flags & JN_GATHER_SHIFT_ALIGNED) != 0;
+  const int shift_pitch = P * set->elem + 16;
+  const bool shift_xform_ok = set->tensor_ok && set->n_slabs == 1 && shift_pitch / 8 <= 256 && P >= 8 &&
+                              (normalize || set->dtype == JN_F32);
   if (engine == JN_ENGINE_AUTO) {
     if (!tma_mode || !out_aligned || !set->bulk_ok) engine = JN_ENGINE_LDG;
-    else if (shifts) engine = shift_tensor_ok ? JN_ENGINE_TENSOR : JN_ENGINE_LDG;
+    else if (shifts) engine = (shift_copy_ok || shift_xform_ok) ? JN_ENGINE_TENSOR : JN_ENGINE_LDG;
     else {
-      // uint8 -> fp32 plain tiles of 256 < P < 1024: per-row bulk copies into 4 x 28 KB stages measured 3-4 %
-      // faster than tensor tiles (profiles/r01/tune_sweep_summary.txt); everywhere else the engines tie or the
-      // tensor tiles win
-      const bool prefer_bulk = normalize && !focus && P > 256 && P < 1024;
+      // uint8 -> fp32 tiles of 256 < P < 1024: per-row bulk copies measured 1-2 % faster than tensor tiles
+      // (two boxes per row); everywhere else the engines tie or the tensor tiles win
+      const bool prefer_bulk = normalize && P > 256 && P < 1024;
       engine = (set->tensor_ok && set->n_slabs == 1 && !prefer_bulk) ? JN_ENGINE_TENSOR : JN_ENGINE_BULK;
     }
   }
   if (shifts && engine == JN_ENGINE_TENSOR)
-    JN_REQUIRE(shift_tensor_ok, "translated gathers on the tensor engine need one slab, patch_size <= 256 and "
-                                "JN_GATHER_SHIFT_ALIGNED (x shifts that are multiples of 16 bytes)");
+    JN_REQUIRE(shift_copy_ok || shift_xform_ok,
+               "translated gathers on the tensor engine need one slab and tile rows of at most 2032 bytes "
+               "(uint8 -> uint8 copies: patch_size <= 256 and JN_GATHER_SHIFT_ALIGNED)");
   if (shifts && engine == JN_ENGINE_BULK)
     return fail(JN_ERR_INVALID, "the bulk engine cannot translate (needs 16-byte aligned row starts); use auto");
   if (engine == JN_ENGINE_TENSOR)
@@ -392,6 +444,8 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
                "tensor-map engine unavailable for this image set / flags (needs one slab, 16-byte aligned rows)");
   if (engine == JN_ENGINE_BULK)
     JN_REQUIRE(tma_mode && out_aligned && set->bulk_ok, "bulk engine needs 16-byte aligned bases, rows and patches");
+  // translated gathers on the xform kernel (superset loads) -- also plain float32 copies that are not vouched for
+  const bool shift_xform = shifts != nullptr && engine == JN_ENGINE_TENSOR && !shift_copy_ok;
 
   if (engine == JN_ENGINE_LDG) {
     a.rows = 1; a.chunks_per_plane = P; a.total_chunks = 0;
@@ -410,8 +464,9 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
   }
 
   // TMA engines: chunk geometry
-  const GatherTune tune = gather_tune(P, set->elem, plain_copy, focus, engine);
-  const int target = plain_copy ? tune.copy_chunk : tune.xform_chunk;
+  const bool use_copy = plain_copy && !shift_xform;
+  const GatherTune tune = gather_tune(P, set->elem, use_copy, focus, engine);
+  const int target = use_copy ? tune.copy_chunk : tune.xform_chunk;
   const int rows = pick_rows(P, set->elem, target, focus);
   JN_REQUIRE(rows > 0, "patch row of %d bytes does not fit a shared-memory stage", P * set->elem);
   a.rows = rows; a.chunks_per_plane = P / rows;
@@ -419,16 +474,25 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
   JN_REQUIRE(total_chunks < (1ll << 31) - (1ll << 22), "jn_gather: too many chunks (%lld)", total_chunks);
   a.total_chunks = (int)total_chunks;
   const size_t chunk_bytes = (size_t)rows * P * set->elem;
+  a.pitch = shift_xform ? shift_pitch : P * set->elem;
+  a.stage_bytes = (int)(((size_t)rows * a.pitch + 127) / 128 * 128);
+  a.wpr_magic = (uint32_t)(((1ull << 32) + (P / 4) - 1) / (P / 4));
+  if (!use_copy) {
+    a.work_counter = next_work_counter(dev.device);
+    if (!a.work_counter) return fail(JN_ERR_CUDA, "cudaMalloc(work counters) failed");
+  }
 
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   if (engine == JN_ENGINE_TENSOR) {
-    if (int rc = encode_slab_map(&map, set->base, set->elem, set->n_images * C, set->height, set->width, set->box_w,
-                                 set->kbox, rows, shifts != nullptr))
+    if (int rc = shift_xform ? encode_shift_map(&map, set->base, set->elem, set->n_images * C, set->height, set->width,
+                                                a.pitch, rows)
+                             : encode_slab_map(&map, set->base, set->elem, set->n_images * C, set->height, set->width,
+                                               set->box_w, set->kbox, rows, shifts != nullptr))
       return rc;
   }
 
-  if (plain_copy) {
+  if (use_copy) {
     const size_t smem = tune.copy_stages * chunk_bytes + jnk::kZeroBytes + tune.copy_stages * sizeof(uint64_t);
     const bool tensor = engine == JN_ENGINE_TENSOR;
 #define JN_COPY(S, D)                                                                                              \
@@ -442,21 +506,22 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
                 tune.copy_ahead);
   }
   const int threads = (kXformWarps + 1) * 32;
-  const bool tensor = engine == JN_ENGINE_TENSOR;
-  const size_t smem = tune.xform_stages * chunk_bytes + 2 * tune.xform_stages * sizeof(uint64_t);
-#define JN_XFORM_S(mode, S)                                                                                        \
-  if (tune.xform_stages == S)                                                                                      \
-    return tensor ? launch_persistent(jnk::gather_xform_kernel<mode, S, kXformWarps, true>, a, map, threads, smem, dev, \
-                                      stream, tune.xform_ctas)                                                     \
-                  : launch_persistent(jnk::gather_xform_kernel<mode, S, kXformWarps, false>, a, map, threads, smem, \
-                                      dev, stream, tune.xform_ctas);
-#define JN_XFORM(mode) JN_XFORM_S(mode, 4) JN_XFORM_S(mode, 2) JN_XFORM_S(mode, 3) JN_XFORM_S(mode, 6) JN_XFORM_S(mode, 8)
+  const int tensor = engine == JN_ENGINE_TENSOR ? 1 : 0;
+  const int stages = tune.xform_stages;
+  JN_REQUIRE(stages >= 2 && stages <= 16, "JN_GATHER_TUNE: xform stages must be 2..16, got %d", stages);
+  const size_t smem = (size_t)stages * (a.stage_bytes + sizeof(jnk::StageDesc) + 2 * sizeof(uint64_t));
+  JN_REQUIRE(smem <= (size_t)dev.max_smem_optin, "xform pipeline of %d x %d bytes does not fit shared memory", stages,
+             a.stage_bytes);
+#define JN_XFORM(mode)                                                                                             \
+  return shift_xform ? launch_persistent(jnk::gather_xform_kernel<mode, kXformWarps, true>, a, map, threads, smem, \
+                                         dev, stream, tune.xform_ctas, stages, tensor)                             \
+                     : launch_persistent(jnk::gather_xform_kernel<mode, kXformWarps, false>, a, map, threads, smem, \
+                                         dev, stream, tune.xform_ctas, stages, tensor);
   if (normalize && !focus) { JN_XFORM(jnk::kNormPlain) }
   else if (normalize && focus) { JN_XFORM(jnk::kNormFocus) }
-  else { JN_XFORM(jnk::kF32Focus) }
+  else if (focus) { JN_XFORM(jnk::kF32Focus) }
+  else { JN_XFORM(jnk::kF32Plain) }
 #undef JN_XFORM
-#undef JN_XFORM_S
-  return fail(JN_ERR_INVALID, "JN_GATHER_TUNE: no xform kernel with %d stages", tune.xform_stages);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -53,6 +53,26 @@ __host__ __device__ __forceinline__ float u8_to_unit(float x) {
 #endif
 }
 
+// The same value from x/256 (exact in float32): x/255 = x/256 + (x/256)/255 is ONE rounding in
+// fma(xs, fl(1/255), xs) -- the error of fl(1/255) is scaled by 1/255 and stays far inside half an ulp
+// (all 256 inputs are compared with u8_to_unit in jn_selftest_host and with torch on the device).
+__host__ __device__ __forceinline__ float unit_from_scaled(float xs) {
+  const float r = 1.0f / 255.0f;
+#ifdef __CUDA_ARCH__
+  return __fmaf_rn(xs, r, xs);
+#else
+  return fmaf(xs, r, xs);
+#endif
+}
+#ifdef __CUDACC__
+// Byte k of a packed word -> value / 255 in three full-rate instructions: PRMT builds the float
+// 32768 + b/256 (one ulp is 2^-8 there), FADD strips the 32768 exactly, FFMA as above.
+template <int k>
+__device__ __forceinline__ float byte_to_unit(uint32_t u) {
+  return unit_from_scaled(__uint_as_float(__byte_perm(u, 0x47000000u, 0x7440 + k)) - 32768.0f);
+}
+#endif
+
 // ---- shared-memory address / mbarrier ------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

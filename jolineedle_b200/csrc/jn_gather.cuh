@@ -47,6 +47,9 @@ struct GatherArgs {
   int chunks_per_plane;         // patch / rows
   int total_chunks;             // n_items * channels * chunks_per_plane
   int box_w, kbox;              // tensor engine: patch = box_w * kbox
+  int pitch, stage_bytes;       // xform kernel: bytes per staged row (patch * elem, + 16 when translating), per stage
+  uint32_t wpr_magic;           // xform kernel: ceil(2^32 / (patch / 4)), division by multiply-high
+  int* work_counter;            // xform kernel: {next unclaimed chunk, CTAs done}; zero before and after a launch
   int skip_negative;            // negative src_index: 1 = leave the output tile untouched, 0 = zero-fill it
 };
 
@@ -171,115 +174,306 @@ gather_copy_kernel(const __grid_constant__ GatherArgs a, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------
-// xform kernel (uint8 -> float32 / Focus)
+// xform kernel (uint8 -> float32, Focus layout, unaligned translation)
 // ------------------------------------------------------------------------------------------
-enum XformMode { kNormPlain = 0, kF32Focus = 1, kNormFocus = 2 };
+// Warp 0 is the TMA producer; the consumer warps read the staged chunk from shared memory,
+// convert and write coalesced vector stores.
+//
+//  * The producer decodes 32 chunks at a time (one per lane: the dependent loads src_index ->
+//    image record / position cost one latency per 32 chunks instead of one per chunk) and hands
+//    each stage a 16-byte descriptor through shared memory, so no consumer touches the index
+//    arrays.  The descriptor is written before the producer's arrive on the stage's `full`
+//    barrier (release) and read after the consumers' wait (acquire).
+//  * kShift: integer translation with ANY x offset.  The TMA unit only takes 16-byte aligned
+//    inner coordinates, so the producer loads the aligned superset of each row (P*elem + 16
+//    bytes, 3-D map of 8-byte elements, out-of-image bytes arrive as zeros) and the consumers
+//    read it back at the residual byte offset (funnel shift for uint8, word select for float32).
+enum XformMode { kNormPlain = 0, kF32Focus = 1, kNormFocus = 2, kF32Plain = 3 };
 
-template <int kMode>
-__device__ __forceinline__ void xform_chunk(const GatherArgs& a, const Chunk& c, const uint8_t* stage, int tid,
+struct __align__(16) StageDesc {
+  unsigned long long dst;  // first byte of the chunk's output item
+  int chrow;               // channel << 16 | first tile row
+  int flags;               // kDescSkip | kDescZero | residual byte offset << 8
+};
+constexpr int kDescSkip = 1, kDescZero = 2, kDescStop = 4;
+
+// 4 staged source pixels of group g of a staged row (uint8: one word; float32: one float4)
+template <bool kShift>
+__device__ __forceinline__ uint32_t staged_u8x4(const uint8_t* row, int g, int off) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(row) + g;
+  if (!kShift) return w[0];
+  w += off >> 2;
+  return __funnelshift_r(w[0], w[1], (off & 3) * 8);
+}
+template <bool kShift>
+__device__ __forceinline__ float4 staged_f32x4(const uint8_t* row, int g, int off) {
+  const float4* v = reinterpret_cast<const float4*>(row) + g;
+  const float4 A = v[0];
+  if (!kShift) return A;
+  const float4 B = v[1];
+  switch (off >> 2) {  // uniform over the CTA
+    case 0: return A;
+    case 1: return make_float4(A.y, A.z, A.w, B.x);
+    case 2: return make_float4(A.z, A.w, B.x, B.y);
+    default: return make_float4(A.w, B.x, B.y, B.z);
+  }
+}
+
+template <int kMode, bool kShift>
+__device__ __forceinline__ void xform_chunk(const GatherArgs& a, const StageDesc& d, const uint8_t* stage, int tid,
                                             int nthreads) {
-  const int P = a.patch;
-  float* out_item = reinterpret_cast<float*>(a.out + (long long)c.item * a.out_item_stride);
-  const bool zero = (c.src == nullptr);
-  if (kMode == kNormPlain) {
-    // chunk = rows*P bytes in, rows*P floats out, both contiguous
-    float* dst = out_item + ((long long)c.channel * P + c.row0) * P;
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(stage);
-    const int n = a.rows * P / 4;
+  // Every iteration is independent of the previous one (row / group of item i come from one multiply-high,
+  // not from a carried counter), so the unrolled body keeps several shared-memory loads in flight.
+  const int P = a.patch, wpr = P >> 2;  // wpr = 4-pixel groups per row
+  const int n = a.rows * wpr, pitch = a.pitch;
+  const uint32_t magic = a.wpr_magic;  // ceil(2^32 / wpr): i / wpr == umulhi(i, magic) for every i < n
+  const int ch = d.chrow >> 16, row0 = d.chrow & 0xFFFF, off = d.flags >> 8;
+  const bool zero = (d.flags & kDescZero) != 0;
+  float* out_item = reinterpret_cast<float*>(d.dst);
+  if (kMode == kNormPlain || kMode == kF32Plain) {
+    // rows * P source pixels in, rows * P floats out, contiguous in the output
+    float* dst = out_item + ((long long)ch * P + row0) * P;
+    if (zero) {
+      for (int i = tid; i < n; i += nthreads) st_f4(dst + 4 * i, 0.f, 0.f, 0.f, 0.f);
+      return;
+    }
 #pragma unroll 4
     for (int i = tid; i < n; i += nthreads) {
-      const uint32_t u = zero ? 0u : w[i];
-      st_f4(dst + 4 * (long long)i, u8_to_unit((float)(u & 0xFF)), u8_to_unit((float)((u >> 8) & 0xFF)),
-            u8_to_unit((float)((u >> 16) & 0xFF)), u8_to_unit((float)(u >> 24)));
+      const uint8_t* row = stage;  // not translated: the stage is contiguous, group i sits at word / float4 i
+      int g = i;
+      if (kShift) {
+        const int r = (int)__umulhi((uint32_t)i, magic);
+        g = i - r * wpr;
+        row = stage + r * pitch;
+      }
+      if (kMode == kNormPlain) {
+        const uint32_t u = staged_u8x4<kShift>(row, g, off);
+        st_f4(dst + 4 * i, byte_to_unit<0>(u), byte_to_unit<1>(u), byte_to_unit<2>(u), byte_to_unit<3>(u));
+      } else {
+        const float4 v = staged_f32x4<kShift>(row, g, off);
+        st_f4(dst + 4 * i, v.x, v.y, v.z, v.w);
+      }
     }
   } else {
-    // Focus: out[(dy + 2*dx) * C + ch][i][j] = tile[ch][2i + dy][2j + dx]
-    const int half = P / 2;
-    const int q4 = P / 4;  // 4-pixel groups per row
-    const int n = a.rows * q4;
-    const long long plane = (long long)half * half;
-#pragma unroll 2
+    // Focus: out[(dy + 2*dx) * C + ch][i][j] = tile[ch][2i + dy][2j + dx]; chunks start on even rows
+    const int half = P >> 1, plane = half * half;
+    const int dy_planes = a.channels * plane, dx_planes = 2 * dy_planes;
+    float* base = out_item + (long long)ch * plane + (row0 >> 1) * half;
+    if (zero) {
+      for (int i = tid; i < n; i += nthreads) {
+        const int r = (int)__umulhi((uint32_t)i, magic), g = i - r * wpr;
+        float* even = base + ((r & 1) * dy_planes + (r >> 1) * half + 2 * g);
+        st_f2(even, 0.f, 0.f);
+        st_f2(even + dx_planes, 0.f, 0.f);
+      }
+      return;
+    }
+#pragma unroll 4
     for (int i = tid; i < n; i += nthreads) {
-      const int r = i / q4, g = i - r * q4;
-      const int y = c.row0 + r;
+      const int r = (int)__umulhi((uint32_t)i, magic), g = i - r * wpr;
+      const uint8_t* row = kShift ? stage + r * pitch : stage;
+      const int gi = kShift ? g : i;
       float e0, o0, e1, o1;
       if (kMode == kF32Focus) {
-        const float4 v = zero ? make_float4(0.f, 0.f, 0.f, 0.f)
-                              : reinterpret_cast<const float4*>(stage)[i];
+        const float4 v = staged_f32x4<kShift>(row, gi, off);
         e0 = v.x; o0 = v.y; e1 = v.z; o1 = v.w;
       } else {
-        const uint32_t u = zero ? 0u : reinterpret_cast<const uint32_t*>(stage)[i];
-        e0 = u8_to_unit((float)(u & 0xFF)); o0 = u8_to_unit((float)((u >> 8) & 0xFF));
-        e1 = u8_to_unit((float)((u >> 16) & 0xFF)); o1 = u8_to_unit((float)(u >> 24));
+        const uint32_t u = staged_u8x4<kShift>(row, gi, off);
+        e0 = byte_to_unit<0>(u); o0 = byte_to_unit<1>(u); e1 = byte_to_unit<2>(u); o1 = byte_to_unit<3>(u);
       }
-      const int dy = y & 1;
-      float* even = out_item + ((long long)(dy * a.channels + c.channel)) * plane + (long long)(y >> 1) * half + 2 * g;
-      float* odd = even + 2ll * a.channels * plane;
+      float* even = base + ((r & 1) * dy_planes + (r >> 1) * half + 2 * g);
       st_f2(even, e0, e1);
-      st_f2(odd, o0, o1);
+      st_f2(even + dx_planes, o0, o1);
     }
   }
 }
 
-template <int kMode, int kStages, int kConsumerWarps, bool kTensor>
+__device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src_lane) {
+  const uint32_t lo = __shfl_sync(0xFFFFFFFFu, (uint32_t)v, src_lane);
+  const uint32_t hi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(v >> 32), src_lane);
+  return ((unsigned long long)hi << 32) | lo;
+}
+
+// What the producer needs to know about one chunk, decoded by one lane.
+struct ChunkPlan {
+  unsigned long long dst, src;  // output item base; first source byte of the chunk (bulk engine)
+  int src_row_bytes;
+  int chrow, flags;             // as in StageDesc
+  int cx, cy, plane;            // tensor-map coordinates
+};
+
+// Image index of chunk q's item (first half of the decode: the only load the second half depends on).
+__device__ __forceinline__ int chunk_image(const GatherArgs& a, int q, bool valid) {
+  if (!valid) return -1;
+  const int item = q / (a.channels * a.chunks_per_plane);
+  return a.src_index ? a.src_index[item] : item;
+}
+
+// Second half of the decode, given the image index: position and image record (independent loads).
+template <bool kShift>
+__device__ __forceinline__ ChunkPlan plan_chunk(const GatherArgs& a, int q, bool valid, int img) {
+  ChunkPlan p;
+  p.dst = p.src = 0; p.src_row_bytes = 0; p.chrow = 0; p.flags = kDescSkip; p.cx = p.cy = p.plane = 0;
+  if (!valid) return p;
+  const int cpi = a.channels * a.chunks_per_plane;
+  const int item = q / cpi;
+  const int rem = q - item * cpi;
+  const int channel = rem / a.chunks_per_plane;
+  const int row0 = (rem - channel * a.chunks_per_plane) * a.rows;
+  p.dst = reinterpret_cast<unsigned long long>(a.out + (long long)item * a.out_item_stride);
+  p.chrow = (channel << 16) | row0;
+  if (img < 0) {  // zero fill, or skip when the caller asked for that
+    p.flags = a.skip_negative ? kDescSkip : kDescZero;
+    return p;
+  }
+  const long long y = a.positions[2 * (long long)item], x = a.positions[2 * (long long)item + 1];
+  const uint8_t* base;
+  int h, w;
+  if (a.images) {
+    const ImageRec r = a.images[img < a.n_images ? img : 0];
+    base = r.base; h = r.height; w = r.width;
+    p.plane = r.plane0 + channel;
+  } else {
+    base = a.base + (long long)img * a.image_stride; h = a.height; w = a.width;
+    p.plane = img * a.channels + channel;
+  }
+  if (img >= a.n_images || y < 0 || x < 0 || (y + 1) * a.patch > h || (x + 1) * a.patch > w) {
+    if (a.status && channel == 0 && row0 == 0) atomicOr(a.status, 1);
+    return p;  // out-of-grid position: reported once, tile skipped
+  }
+  p.flags = 0;
+  const int px = (int)x, py = (int)y;
+  const int sy = a.shifts ? a.shifts[2 * img] : 0, sx = a.shifts ? a.shifts[2 * img + 1] : 0;
+  p.src_row_bytes = w * a.elem;
+  p.src = reinterpret_cast<unsigned long long>(base + (((long long)channel * h + y * a.patch + row0) * w + x * a.patch) * a.elem);
+  if (kShift) {
+    const int xb = (px * a.patch - sx) * a.elem;  // byte offset of the tile's first pixel in its image row
+    const int xa = xb & ~15;                       // 16-byte floor (also for negative offsets)
+    p.flags |= (xb - xa) << 8;
+    p.cx = xa >> 3;                                // in 8-byte map elements
+    p.cy = py * a.patch + row0 - sy;
+  } else {
+    p.cx = px * a.kbox;
+    p.cy = py * a.patch + row0;
+  }
+  return p;
+}
+
+template <int kMode, int kConsumerWarps, bool kShift>
 __global__ void __launch_bounds__((kConsumerWarps + 1) * 32)
-gather_xform_kernel(const __grid_constant__ GatherArgs a, const __grid_constant__ CUtensorMap map0) {
+gather_xform_kernel(const __grid_constant__ GatherArgs a, const __grid_constant__ CUtensorMap map0, const int stages,
+                    const int tensor) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t chunk_bytes = (uint32_t)a.rows * a.patch * a.elem;
+  const uint32_t tx_bytes = (uint32_t)a.rows * a.pitch;
   const uint32_t row_bytes = (uint32_t)a.patch * a.elem;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * chunk_bytes);
-  uint64_t* empty = full + kStages;
+  StageDesc* desc = reinterpret_cast<StageDesc*>(smem + (size_t)stages * a.stage_bytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(desc + stages);
+  uint64_t* empty = full + stages;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], kConsumerWarps);
     }
     fence_mbar_init();
-    if (kTensor) prefetch_tensormap(&map0);
+    if (tensor) prefetch_tensormap(&map0);
   }
   __syncthreads();
 
-  const int grid = gridDim.x;
-  const int mine = a.total_chunks > (int)blockIdx.x ? (a.total_chunks - (int)blockIdx.x + grid - 1) / grid : 0;
+  int st = 0;
+  uint32_t phase = 0;  // parity of the ring round this warp is in
 
   if (warp == 0) {  // ---- TMA producer
-    for (int j = 0; j < mine; ++j) {
-      const int st = j % kStages;
-      uint8_t* stage = smem + (size_t)st * chunk_bytes;
-      if (j >= kStages) mbar_wait(&empty[st], (uint32_t)(j / kStages - 1) & 1u);
-      Chunk c;
-      const bool skip = decode_chunk(a, (int)blockIdx.x + j * grid, c);
-      if (c.src != nullptr && !skip) {
-        if (lane == 0) mbar_arrive_expect_tx(&full[st], chunk_bytes);
-        __syncwarp();
-        if (kTensor) {
-          if (lane == 0) {
-            const CUtensorMap* m = &map0;
-            if (a.shifts)  // 3-D map [W, H, planes]: x offsets in 16-byte steps, any y; out-of-image pixels arrive as zeros
-              tensor_g2s_3d(stage, m, c.px * a.patch - c.sx, c.py * a.patch + c.row0 - c.sy, c.plane, &full[st]);
-            else
-              tensor_g2s_4d(stage, m, 0, c.px * a.kbox, c.py * a.patch + c.row0, c.plane, &full[st]);
-          }
-        } else {
-          for (int r = lane; r < a.rows; r += 32)
-            bulk_g2s(stage + (size_t)r * row_bytes, c.src + (long long)r * c.src_row_bytes, row_bytes, &full[st]);
+    // Chunks are claimed from a global counter (a statically dealt grid drifts apart: SMs that see a faster
+    // memory path finish early and leave a tail), in batches that shrink towards the end of the launch:
+    // up to 32 chunks (one per lane, decoded in parallel) early on, 4 at the end.
+    const int total = a.total_chunks, grid = gridDim.x;
+    auto claim = [&](int& base, int& size) {
+      int b = 0, n = 0;
+      if (lane == 0) {
+        const int seen = *reinterpret_cast<volatile int*>(a.work_counter);
+        n = seen < total ? min(32, max(4, (total - seen) / (2 * grid))) : 1;
+        b = atomicAdd(a.work_counter, n);
+      }
+      base = __shfl_sync(0xFFFFFFFFu, b, 0);
+      size = __shfl_sync(0xFFFFFFFFu, n, 0);
+    };
+    auto plan = [&](int base, int size) {
+      const int q = base + lane;
+      const bool valid = lane < size && q < total;
+      return plan_chunk<kShift>(a, q, valid, chunk_image(a, q, valid));
+    };
+    // software pipeline: while batch b is issued, the loads that decode batch b+1 are in flight
+    int base, size;
+    claim(base, size);
+    ChunkPlan cur = plan(base, size);
+    bool ring_used = false;  // true once every stage has been filled once
+    while (base < total) {
+      int next_base, next_size;
+      claim(next_base, next_size);
+      const ChunkPlan nxt = plan(next_base, next_size);
+      const int count = min(size, total - base);
+      for (int k = 0; k < count; ++k) {
+        const int flags = __shfl_sync(0xFFFFFFFFu, cur.flags, k);
+        const int chrow = __shfl_sync(0xFFFFFFFFu, cur.chrow, k);
+        const int cx = __shfl_sync(0xFFFFFFFFu, cur.cx, k), cy = __shfl_sync(0xFFFFFFFFu, cur.cy, k);
+        const int plane = __shfl_sync(0xFFFFFFFFu, cur.plane, k);
+        const int src_row_bytes = __shfl_sync(0xFFFFFFFFu, cur.src_row_bytes, k);
+        const unsigned long long dst = shfl_u64(cur.dst, k);
+        const unsigned long long src = shfl_u64(cur.src, k);
+        uint8_t* stage = smem + (size_t)st * a.stage_bytes;
+        if (ring_used) mbar_wait(&empty[st], phase ^ 1u);
+        if (lane == 0) {
+          StageDesc d;
+          d.dst = dst; d.chrow = chrow; d.flags = flags;
+          desc[st] = d;
         }
-      } else if (lane == 0) {
-        mbar_arrive(&full[st]);
+        if ((flags & (kDescSkip | kDescZero)) == 0) {
+          if (lane == 0) mbar_arrive_expect_tx(&full[st], tx_bytes);
+          __syncwarp();
+          if (tensor) {
+            if (lane == 0) {
+              if (kShift) tensor_g2s_3d(stage, &map0, cx, cy, plane, &full[st]);
+              else tensor_g2s_4d(stage, &map0, 0, cx, cy, plane, &full[st]);
+            }
+          } else {
+            const uint8_t* from = reinterpret_cast<const uint8_t*>(src);
+            for (int r = lane; r < a.rows; r += 32)
+              bulk_g2s(stage + (size_t)r * row_bytes, from + (long long)r * src_row_bytes, row_bytes, &full[st]);
+          }
+        } else if (lane == 0) {
+          mbar_arrive(&full[st]);  // nothing to load: complete the phase by hand
+        }
+        if (++st == stages) { st = 0; phase ^= 1u; ring_used = true; }
+      }
+      cur = nxt; base = next_base; size = next_size;
+    }
+    // tell the consumers to leave, then clean the counters up for the next launch: the last CTA whose claims
+    // have all come back empty knows that nobody will touch them again
+    if (ring_used) mbar_wait(&empty[st], phase ^ 1u);
+    if (lane == 0) {
+      StageDesc d;
+      d.dst = 0; d.chrow = 0; d.flags = kDescStop;
+      desc[st] = d;
+      mbar_arrive(&full[st]);
+      if (atomicAdd(a.work_counter + 1, 1) == (int)gridDim.x - 1) {
+        a.work_counter[1] = 0;
+        __threadfence();
+        a.work_counter[0] = 0;
       }
     }
   } else {  // ---- consumers
     const int tid = threadIdx.x - 32;
-    for (int j = 0; j < mine; ++j) {
-      const int st = j % kStages;
-      Chunk c;
-      const bool skip = decode_chunk(a, (int)blockIdx.x + j * grid, c);
-      mbar_wait(&full[st], (uint32_t)(j / kStages) & 1u);
-      if (!skip) xform_chunk<kMode>(a, c, smem + (size_t)st * chunk_bytes, tid, kConsumerWarps * 32);
+    for (;;) {
+      mbar_wait(&full[st], phase);
+      const StageDesc d = desc[st];
+      if (d.flags & kDescStop) break;
+      if ((d.flags & kDescSkip) == 0)
+        xform_chunk<kMode, kShift>(a, d, smem + (size_t)st * a.stage_bytes, tid, kConsumerWarps * 32);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[st]);
+      if (++st == stages) { st = 0; phase ^= 1u; }
     }
   }
 }

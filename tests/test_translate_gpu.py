@@ -15,22 +15,25 @@ def crops_of(images, pos, src, P):
                         for (y, x), k in zip(pos.tolist(), src.tolist())])
 
 
-@pytest.mark.parametrize("engine", ["auto", "tensor", "ldg"])
+@pytest.mark.parametrize("engine", ["auto", "tensor", "tensor-aligned", "ldg"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.uint8])
 @pytest.mark.parametrize("P,gh,gw", [(64, 4, 5), (256, 3, 3), (448, 2, 3)])
 def test_gather_with_translation(engine, dtype, P, gh, gw):
+    """auto / tensor: arbitrary x offsets ride the TMA engine through 16-byte aligned superset loads
+    (xform kernel); tensor-aligned: x offsets the caller vouches for, pure-DMA copy kernel; ldg: plain loads."""
     from jolineedle_b200.gather import ImageSet
 
-    if engine == "tensor" and P > 256:
-        pytest.skip("translated tiles wider than one TMA box (256 elements) run on the plain-load engine")
+    aligned = engine == "tensor-aligned"
+    if aligned and P > 256:
+        pytest.skip("the pure-DMA translated copy needs tiles of one TMA box (256 elements)")
+    engine = "tensor" if aligned else engine
     b = 5
     g = torch.Generator().manual_seed(P)
     u8 = torch.randint(0, 256, (b, 3, gh * P, gw * P), dtype=torch.uint8, generator=g)
     images = u8 if dtype == torch.uint8 else u8.float() / 255
     # (tx, ty): none, small, negative, larger than a patch, and far enough to empty whole tiles
     shifts_xy = np.array([(0, 0), (13, -7), (-P // 3, P // 5), (P + 9, -(P + 3)), (-(gw * P - 5), gh * P - 2)])
-    aligned = engine == "tensor"
-    if aligned:  # the TMA unit only takes x offsets that are multiples of 16 bytes; y is free
+    if aligned:  # x offsets that are multiples of 16 bytes; y is free
         shifts_xy[:, 0] = (shifts_xy[:, 0] // 16) * 16
     shifted = translate_oracle(images, shifts_xy)
     s = ImageSet(images.cuda(), P)
@@ -40,8 +43,14 @@ def test_gather_with_translation(engine, dtype, P, gh, gw):
     src = torch.from_numpy(rng.integers(0, b, n).astype(np.int32))
     d_shifts = torch.from_numpy(shifts_xy[:, ::-1].copy().astype(np.int32)).cuda()  # kernels take (ty, tx)
     table = torch.from_numpy(load_golden("norm.npz")["u8_over_255"])
-    for normalize, focus in ((False, False), (dtype == torch.uint8, False), (dtype == torch.uint8, True)):
-        if focus and dtype == torch.float32:
+    u8_in = dtype == torch.uint8
+    for normalize, focus in ((False, False), (u8_in, False), (u8_in, True), (False, True)):
+        if focus and not normalize and u8_in:
+            continue  # uint8 -> uint8 Focus is nobody's layout
+        if engine == "tensor" and not aligned and u8_in and not normalize:
+            # uint8 -> uint8 copies have no register pass that could realign them: only vouched-for offsets
+            with pytest.raises(ValueError):
+                s.gather(pos.cuda(), src_index=src.cuda(), shifts=d_shifts, engine="tensor")
             continue
         want = crops_of(shifted, pos, src, P)
         if normalize:
@@ -51,10 +60,6 @@ def test_gather_with_translation(engine, dtype, P, gh, gw):
         got = s.gather(pos.cuda(), src_index=src.cuda(), shifts=d_shifts, shifts_aligned=aligned, normalize=normalize,
                        focus=focus, engine=engine)
         assert torch.equal(got.cpu(), want), (engine, dtype, P, normalize, focus)
-    if dtype == torch.float32:
-        got = s.gather(pos.cuda(), src_index=src.cuda(), shifts=d_shifts, shifts_aligned=aligned, focus=True,
-                       engine=engine)
-        assert torch.equal(got.cpu(), focus_restatement(crops_of(shifted, pos, src, P)))
 
 
 def test_bulk_engine_refuses_translation_and_lists_fall_back():
@@ -67,9 +72,8 @@ def test_bulk_engine_refuses_translation_and_lists_fall_back():
     shifts = torch.tensor([[5, -9], [-70, 3]], dtype=torch.int32).cuda()  # (ty, tx)
     with pytest.raises(ValueError):
         s.gather(pos, shifts=shifts, engine="bulk")
-    with pytest.raises(ValueError):  # the tensor engine needs the caller's word that x shifts are 16-byte aligned
-        ImageSet(torch.rand(2, 3, 2 * P, 2 * P).cuda(), P).gather(pos[:, :1].repeat(1, 2) * 0, shifts=shifts,
-                                                                  engine="tensor")
+    with pytest.raises(ValueError):  # lists of images have no single tensor map
+        s.gather(pos, shifts=shifts, engine="tensor")
     got = s.gather(pos, shifts=shifts)  # auto -> plain loads for a list of images
     for i, im in enumerate(imgs):
         ty, tx = shifts[i].tolist()

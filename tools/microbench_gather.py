@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from jolineedle_b200.gather import ImageSet  # noqa: E402
 
 
-def bench_one(P, n, dtype, normalize, focus, engine, iters=10, pool_bytes=6 << 30):
+def bench_one(P, n, dtype, normalize, focus, engine, iters=10, pool_bytes=6 << 30, translate=False):
     elem = 1 if dtype == torch.uint8 else 4
     gh = gw = max(2, 2048 // P)
     img_bytes = 3 * gh * P * gw * P * elem
@@ -31,21 +31,24 @@ def bench_one(P, n, dtype, normalize, focus, engine, iters=10, pool_bytes=6 << 3
     cell = (idx // n_img) % (gh * gw)
     pos = torch.stack([cell // gw, cell % gw], 1).contiguous()
     out_elem = 4 if (normalize or dtype == torch.float32) else 1
+    shifts = None
+    if translate:  # arbitrary integer (ty, tx) per image within half a patch (zero fill at the borders)
+        shifts = torch.randint(-P // 2, P // 2 + 1, (n_img, 2), generator=torch.Generator().manual_seed(1)).int().cuda()
     out = torch.empty(s.out_shape(n, focus), dtype=s.out_dtype(normalize), device="cuda")
     for _ in range(3):
-        s.gather(pos, src_index=src, out=out, normalize=normalize, focus=focus, engine=engine)
+        s.gather(pos, src_index=src, out=out, normalize=normalize, focus=focus, engine=engine, shifts=shifts)
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
     ev[0].record()
     for i in range(iters):
-        s.gather(pos, src_index=src, out=out, normalize=normalize, focus=focus, engine=engine)
+        s.gather(pos, src_index=src, out=out, normalize=normalize, focus=focus, engine=engine, shifts=shifts)
         ev[i + 1].record()
     torch.cuda.synchronize()
     times = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
     ms = times[len(times) // 2]
     bytes_ = n * 3 * P * P * (elem + out_elem)
     return {"P": P, "n": n, "src": "u8" if elem == 1 else "f32", "normalize": normalize, "focus": focus,
-            "engine": engine, "ms": round(ms, 4), "GBps": round(bytes_ / ms / 1e6, 1),
+            "engine": engine, "translate": translate, "ms": round(ms, 4), "GBps": round(bytes_ / ms / 1e6, 1),
             "tiles_per_s": round(n / ms * 1e3), "out_MB": round(n * 3 * P * P * out_elem / 1e6)}
 
 
@@ -59,6 +62,7 @@ def main():
     ap.add_argument("--modes", default="f32,u8", help="f32 = fp32 copy, u8 = uint8 normalised")
     ap.add_argument("--layouts", default="plain,focus")
     ap.add_argument("--label", default="")
+    ap.add_argument("--translate", action="store_true", help="per-image integer translation folded into the gather")
     args = ap.parse_args()
     peak = 6465.2
     try:
@@ -83,7 +87,7 @@ def main():
     lines = []
     for c in combos:
         try:
-            r = bench_one(*c)
+            r = bench_one(*c, translate=args.translate)
             r["frac_of_measured_peak"] = round(r["GBps"] / peak, 3)
             if args.label:
                 r["label"] = args.label

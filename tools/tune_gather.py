@@ -10,13 +10,13 @@ from jolineedle_b200.gather import ImageSet  # noqa: E402
 PEAK = 6465.2
 
 
-def time_gather(s, pos, src, out, normalize, focus, engine, iters=7):
+def time_gather(s, pos, src, out, normalize, focus, engine, iters=7, shifts=None):
     for _ in range(3):
-        s.gather(pos, src_index=src, out=out, normalize=normalize, focus=focus, engine=engine)
+        s.gather(pos, src_index=src, out=out, normalize=normalize, focus=focus, engine=engine, shifts=shifts)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
     ev[0].record()
     for i in range(iters):
-        s.gather(pos, src_index=src, out=out, normalize=normalize, focus=focus, engine=engine)
+        s.gather(pos, src_index=src, out=out, normalize=normalize, focus=focus, engine=engine, shifts=shifts)
         ev[i + 1].record()
     torch.cuda.synchronize()
     t = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--patches", default="448,256,128,1024")
     ap.add_argument("--out", default="gpurun_out/tune_sweep.jsonl")
     ap.add_argument("--crop-gb", type=float, default=2.0)
+    ap.add_argument("--skip-copy", action="store_true", help="only the xform kernel's modes")
+    ap.add_argument("--translate", action="store_true", help="per-image integer translation (xform kernel, tensor engine)")
     args = ap.parse_args()
     results = []
     for P in [int(v) for v in args.patches.split(",")]:
@@ -46,9 +48,14 @@ def main():
             cell = (idx // n_img) % (gh * gw)
             pos = torch.stack([cell // gw, cell % gw], 1).contiguous()
             normalize = dtype == torch.uint8
+            shifts = None
+            if args.translate:
+                shifts = torch.randint(-P // 2, P // 2 + 1, (n_img, 2), generator=torch.Generator().manual_seed(1)).int().cuda()
             for focus in (False, True):
                 out = torch.empty(s.out_shape(n, focus), dtype=torch.float32, device="cuda")
-                copy_mode = (not normalize) and (not focus)
+                copy_mode = (not normalize) and (not focus) and not args.translate
+                if copy_mode and args.skip_copy:
+                    continue
                 row = P * elem
                 if copy_mode:
                     grid = [(S, D, ch, c) for (S, D) in ((2, 1), (3, 1), (3, 2), (4, 2), (4, 3), (6, 3), (6, 4), (8, 4), (12, 6))
@@ -56,20 +63,20 @@ def main():
                             if 4096 <= ch <= 65536 and (S * ch + 4200) * c <= 227 * 1024 and ch // row <= min(P, 256) and P % (ch // row) == 0]
                     tunes = [f"{S},{D},{ch},{c},0,0,0" for (S, D, ch, c) in grid]
                 else:
-                    grid = [(S, ch, c) for S in (2, 3, 4, 6) for ch in (row * 8, row * 16, row * 32, row * 64, row * 128)
+                    grid = [(S, ch, c) for S in (2, 3, 4, 6, 8) for ch in (row * 8, row * 16, row * 32, row * 64, row * 128)
                             for c in (1, 2, 3, 4)
                             if 4096 <= ch <= 65536 and (S * ch + 256) * c <= 227 * 1024 and ch // row <= min(P, 256) and P % (ch // row) == 0]
                     tunes = [f"0,0,0,0,{S},{ch},{c}" for (S, ch, c) in grid]
                 nbytes = n * 3 * P * P * (elem + 4)
-                for engine in ("tensor", "bulk"):
+                for engine in (("tensor",) if args.translate else ("tensor", "bulk")):
                     shape_rows = []
                     for t in tunes:
                         os.environ["JN_GATHER_TUNE"] = t
                         try:
-                            ms = time_gather(s, pos, src, out, normalize, focus, engine)
+                            ms = time_gather(s, pos, src, out, normalize, focus, engine, shifts=shifts)
                         except Exception as e:
                             continue
-                        r = {"P": P, "src": "u8" if elem == 1 else "f32", "focus": focus, "engine": engine, "tune": t,
+                        r = {"P": P, "src": "u8" if elem == 1 else "f32", "focus": focus, "engine": engine, "translate": bool(args.translate), "tune": t,
                              "ms": round(ms, 4), "GBps": round(nbytes / ms / 1e6, 1)}
                         shape_rows.append(r)
                     results.extend(shape_rows)
