@@ -14,6 +14,7 @@ The device half (:func:`expand_packed`) is shared: K0 5 %-area bitmaps, K3 ``jn_
 """
 import ctypes
 import random
+from itertools import chain
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -22,6 +23,8 @@ import torch
 from .. import _cabi
 from ..gather import ImageSet
 from ..utils import Position
+
+_chain = chain.from_iterable
 
 
 class PackedPlans:
@@ -44,8 +47,9 @@ def boxes_array(bboxes: Sequence[Sequence], n_max: Optional[int] = None):
     total = int(counts.sum())
     if total == 0:
         return arr, counts, n_max, True
-    # one conversion for the whole batch: BBox = ((y1, x1), (y2, x2)) -> [total, 2, 2]
-    flat = np.asarray([b for boxes in bboxes for b in boxes])
+    # one conversion for the whole batch: BBox = ((y1, x1), (y2, x2)) -> flat list of 4 * total numbers
+    # (flattening in python first is ~10x faster than letting numpy walk the nested tuples)
+    flat = np.array(list(_chain(_chain(_chain(bboxes)))))
     exact = bool(np.issubdtype(flat.dtype, np.integer)) or bool(np.all(flat == np.floor(flat)))
     flat = flat.reshape(total, 4)[:, [1, 0, 3, 2]].astype(np.int64)  # -> x1, y1, x2, y2 (truncation like `.int()`)
     image = np.repeat(np.arange(n), counts)
@@ -123,9 +127,12 @@ def plan_native(boxes: np.ndarray, n_boxes: np.ndarray, n_max: int, rows: np.nda
     seed_arr = np.zeros(n, dtype=np.uint64)
     has_seed = np.zeros(n, dtype=np.uint8)
     if seeds is not None:
-        for i, s in enumerate(seeds):
-            if s is not None:
-                seed_arr[i], has_seed[i] = int(s), 1
+        if None not in seeds:
+            seed_arr, has_seed = np.array(seeds, dtype=np.uint64), np.ones(n, dtype=np.uint8)
+        else:
+            for i, s in enumerate(seeds):
+                if s is not None:
+                    seed_arr[i], has_seed[i] = int(s), 1
     start = None
     if position is not None:
         start = np.tile(np.array([int(position[0]), int(position[1])], dtype=np.int32), (n, 1))
