@@ -6,7 +6,8 @@
 
 Default workload = BASELINE.json configs[1]: supervised trajectories on LARD-shaped images
 (2048x2448 zero-padded to 2240x2688), patch 448, max-seq-len 8, 256 images per GPU, binomial
-key points 0-3.  One *step* = one call of ``generate_trajectories`` on a fresh batch of seeds
+key points 0-3; uint8 images normalised by the gather (``--src f32`` feeds pre-normalised float32
+images instead: same crops bit for bit, 4x the source bytes).  One *step* = one call of ``generate_trajectories`` on a fresh batch of seeds
 (host plan + K0 + K3 + K1).  ``--workload reinforce`` runs BASELINE configs[2] instead (B=1024
 episodes, T=20, STOP enabled): one step = reset + T env steps with seeded random actions.
 
@@ -339,7 +340,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="supervised", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="episodes per GPU (default: the BASELINE config's)")
-    ap.add_argument("--src", default="f32", choices=["f32", "u8"], help="resident image dtype")
+    ap.add_argument("--src", default="u8", choices=["f32", "u8"],
+                    help="image dtype: u8 = uint8 images normalised by the gather (x/255 like ToTensor, bit-identical "
+                         "crops; SURVEY 8d's primary synthetic input), f32 = pre-normalised float32 images as the "
+                         "reference's dataset hands them over")
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-pool", type=int, default=0,
@@ -440,10 +444,13 @@ def main():
     traffic, traffic_src = None, None
     try:
         summary = json.load(open(os.path.join(ROOT, "profiles", "r01", "ncu_summary.json")))
-        prefix = "gather_copy_kernel" if args.workload == "supervised" and src == "f32" else None
-        if prefix and wl.batch == default_batch:
-            rec = next(v[0] for k_, v in summary["supervised"].items() if k_.startswith(prefix))
-            traffic, traffic_src = int(rec["dram_traffic_bytes"]), "profiles/r01/ncu_summary.json (ncu --set full)"
+        capture = summary[f"{args.workload}_{src}"]
+        prefix = "gather_xform_kernel" if src == "u8" else "gather_copy_kernel"
+        if wl.batch == default_batch:  # the capture was taken at the default batch
+            recs = [r for k_, v in capture.items() if k_.startswith(prefix) for r in v]
+            rec = max(recs, key=lambda r: r["duration_s"])  # the trajectory / step gather (detection gathers are smaller)
+            traffic = int(rec["dram_traffic_bytes"])
+            traffic_src = f"profiles/r01/ncu_summary.json[{args.workload}_{src}] (ncu --set full)"
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
