@@ -61,6 +61,16 @@ def device_images(b, h, w, seed, device, dtype):
     return out
 
 
+def read_back(tensors, non_blocking):
+    """Device -> pinned host copies of a step's results; returns (host tensors, bytes)."""
+    host = {}
+    for k, v in tensors.items():
+        dst = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+        dst.copy_(v, non_blocking=non_blocking)
+        host[k] = dst
+    return host, sum(v.numel() * v.element_size() for v in host.values())
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -167,11 +177,10 @@ class SupervisedWorkload:
         tile = 3 * P * P
         return valid_items * tile * (s_in + 4) + (n_items - valid_items) * tile * 4  # padded slots: zero-fill writes
 
-    def d2h(self, out):
+    def d2h(self, out, non_blocking=False):
         """What a trainer reads back on the host per step (actions/positions/masks/labels)."""
         keys = ("current_actions", "next_actions", "positions", "masks", "labels")
-        host = {k: out[k].cpu() for k in keys}
-        return host, sum(v.numel() * v.element_size() for v in host.values())
+        return read_back({k: out[k] for k in keys}, non_blocking)
 
     # --- CPU reference port (oracle) on a bounded sample
     def cpu_sample(self, n_episodes, step):
@@ -240,17 +249,19 @@ class ReinforceWorkload:
         env = NeedleGeneralEnv(imgs, self.boxes, self.PATCH, self.T, 1, stop_enabled=True,
                                normalize=(self.src_dtype == "u8"), history=True, device=device,
                                translate=self.translate)
-        torch.manual_seed(step * 31 + self.rank)
+        # (seeds the CPU generator reset() draws its start positions from; torch.manual_seed would also walk
+        # through every accelerator backend, 0.1 ms a call)
+        torch.default_generator.manual_seed(step * 31 + self.rank)
         self.gen.manual_seed(step * 31 + self.rank)
         b = self.batch
-        rewards = torch.empty((self.T, b), dtype=torch.float32, device=self.device)
-        term = torch.empty((self.T, b), dtype=torch.bool, device=self.device)
+        actions = torch.randint(0, 9, (self.T, b), device=self.device, generator=self.gen)  # the policy's stand-in
+        rewards, term = [], []
         env.reset()
         for t in range(self.T):
-            a = torch.randint(0, 9, (b,), device=self.device, generator=self.gen)
-            _, r, te, _, _ = env.step(a)
-            rewards[t] = r
-            term[t] = te
+            _, r, te, _, _ = env.step(actions[t])
+            rewards.append(r)
+            term.append(te)
+        rewards, term = torch.stack(rewards), torch.stack(term)  # [T, B] as the trainer collects them
         out = rollout_tail(rewards, term)
         out["positions"] = env.positions
         return out
@@ -262,9 +273,8 @@ class ReinforceWorkload:
         s_in = 1 if self.src_dtype == "u8" else 4
         return n_items * 3 * self.PATCH * self.PATCH * (s_in + 4)
 
-    def d2h(self, out):
-        host = {k: out[k].cpu() for k in ("rewards", "returns", "masks")}
-        return host, sum(v.numel() * v.element_size() for v in host.values())
+    def d2h(self, out, non_blocking=False):
+        return read_back({k: out[k] for k in ("rewards", "returns", "masks")}, non_blocking)
 
     def cpu_sample(self, n_episodes, step):
         from oracle.gaze_oracle import GazeOracle, returns_oracle
@@ -439,6 +449,10 @@ def main():
         dur.append(e0.elapsed_time(e1))
         byts.append(wl.gather_bytes(n_items, v, tag))
     achieved = (sum(byts) / len(byts)) / (sum(dur) / len(dur) / 1e3) / 1e9 if dur else 0.0
+    by_tag = {}
+    for tag, n_items, e0, e1 in timing:
+        by_tag.setdefault(tag, []).append(e0.elapsed_time(e1))
+    gather_ms = {tag: round(sum(v) / len(v), 4) for tag, v in by_tag.items()}  # mean launch time of every gather
     # DRAM traffic per launch of that kernel from the committed `ncu --set full` capture of this workload at its
     # default batch (profiles/r01/ncu_summary.json, produced by tools/gpu_ci.sh ncu); null when there is none
     traffic, traffic_src = None, None
@@ -474,24 +488,55 @@ def main():
             host = pinned(wl.images)
         full = sum(t.numel() * t.element_size() for t in host) if isinstance(host, list) else host.numel() * host.element_size()
         zero_copy = args.workload == "supervised"  # pinned lists are gathered in place; batched RL images are uploaded
+        wl_patch = getattr(wl, "PATCH", P)
         e2e_steps = max(2, min(args.steps, 5))
         wl.run(0, images=host, device=device)
         barrier()
         eunits, d2h_bytes, h2d = 0.0, 0, 0
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record()
-        for s in range(e2e_steps):
-            out = wl.run(args.warmup + s, images=host, device=device)
-            hostres, d2h_bytes = wl.d2h(out)  # synchronising device -> host read of the step's result
-            if zero_copy:  # tiles actually read over PCIe: recorded trajectory slots + detection patches
+        side = torch.cuda.Stream(device)
+        tile_bytes = 3 * wl_patch * wl_patch * (1 if src == "u8" else 4)
+
+        def launch(step):
+            """Host plan + launches of one step (asynchronous); its device -> host read is queued on a side
+            stream behind an event, so that it overlaps the next step's PCIe reads like a prefetching trainer."""
+            out = wl.run(step, images=host, device=device)
+            stats = dict(getattr(wl, "stats", {}))
+            done = torch.cuda.Event()
+            done.record()
+            with torch.cuda.stream(side):
+                side.wait_event(done)
+                hostres, nbytes = wl.d2h(out, non_blocking=True)
+                counts = None
+                if zero_copy:  # tiles that crossed PCIe: first occurrences of trajectory slots + unseen detection patches
+                    zero = torch.zeros((), dtype=torch.long, device=device)
+                    tiles = torch.stack([stats.get("host_traj_tiles", zero), stats.get("host_det_tiles", zero)])
+                    counts = read_back({"tiles": tiles}, True)[0]["tiles"]
+                read = torch.cuda.Event()
+                read.record(side)
+            return out, hostres, nbytes, counts, read
+
+        def finish(pending):
+            nonlocal eunits, d2h_bytes, h2d
+            out, hostres, nbytes, counts, read = pending
+            read.synchronize()  # the step's results are on the host
+            d2h_bytes = nbytes
+            if zero_copy:
                 eunits += float(hostres["masks"].sum())
-                # (detection patches that repeat a trajectory glimpse are copied inside HBM, not re-read from the host)
-                det_tiles = wl.stats.get("host_det_tiles", out["patches_yolox"].shape[0])
-                tiles = float(hostres["masks"].sum()) + float(det_tiles)
-                h2d += tiles * 3 * P * P * (1 if src == "u8" else 4)
+                h2d += float(counts.sum()) * tile_bytes
             else:
                 eunits += float(wl.batch * (wl.T + 1))
                 h2d += full
+
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        pending = None
+        for s in range(e2e_steps):
+            nxt = launch(args.warmup + s)
+            if pending is not None:
+                finish(pending)
+            pending = nxt
+        finish(pending)
+        torch.cuda.current_stream(device).wait_stream(side)
         t1.record()
         barrier()
         ems = max_over_ranks(t0.elapsed_time(t1), device)
@@ -530,7 +575,7 @@ def main():
                              "writes GBs of crops",
                        "parallelism": f"episodes sharded over {world} GPU(s), no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks.summary(), "host_ms_per_step": host_ms,
+            "clocks": clocks.summary(), "host_ms_per_step": host_ms, "gather_ms_by_tag": gather_ms,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

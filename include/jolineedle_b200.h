@@ -47,6 +47,9 @@ typedef enum jn_dtype { JN_U8 = 0, JN_F32 = 1 } jn_dtype;
 #define JN_GATHER_FOCUS 2u     /* output in YOLOX Focus space-to-depth layout [4*C, P/2, P/2] */
 #define JN_GATHER_SHIFT_ALIGNED 4u /* caller guarantees every x shift is a multiple of 16 bytes (TMA may serve it) */
 #define JN_GATHER_SKIP_NEGATIVE 8u /* items with a negative src_index are left untouched instead of zero-filled */
+/* src_index values: >= 0 image; -1 zero-filled tile (left untouched with JN_GATHER_SKIP_NEGATIVE);
+ * <= JN_SRC_SKIP tile always left untouched */
+#define JN_SRC_SKIP (-2)
 
 /* jn_gather engine selection (JN_ENGINE_AUTO picks the fastest one the shapes allow) */
 typedef enum jn_engine {
@@ -235,6 +238,16 @@ int jn_traj_expand(const int32_t* start_yx /*[n,2]*/, const int32_t* seg_begin /
 int jn_tile_lookup(const int64_t* traj_positions, const int32_t* traj_src, int T,
                    const int64_t* query_positions, const int32_t* query_src, int n_queries,
                    int slab_base, int64_t* out_positions, int32_t* out_src, void* stream);
+
+/* First occurrences and repeats among the recorded slots of each episode (traj_positions / traj_src as
+ * written by jn_traj_expand, n_slots = n * T).  A slot whose patch was already recorded at an earlier
+ * slot of its episode gets first_src = JN_SRC_SKIP and repeat_src = index of that earlier slot; all
+ * other slots keep traj_src in first_src and get repeat_src = JN_SRC_SKIP.  Gathering first_src out of
+ * the images and then repeat_src out of the [n*T, C, P, P] buffer itself (as a set of one-patch images,
+ * patch (0, 0)) yields the same buffer as one gather of traj_src (generate_sample's crops,
+ * simple_env.py:560-572), but a revisited tile of a host-resident image crosses PCIe once. */
+int jn_tile_dedupe(const int64_t* traj_positions, const int32_t* traj_src, int n_slots, int T,
+                   int32_t* first_src, int32_t* repeat_src, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Host-side planner of supervised episodes (no GPU involved; all pointers are HOST memory).

@@ -54,6 +54,7 @@ SIGNATURES = {
     "jn_traj_expand": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, c_int, c_int, _P, _P, _P, _P, _P, _P,
                                _P, _P, _P]),
     "jn_tile_lookup": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, _P, _P, _P]),
+    "jn_tile_dedupe": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
     "jn_plan_create": (c_int, [POINTER(_P)]),
     "jn_plan_destroy": (None, [_P]),
     "jn_plan_error": (c_char_p, [_P]),
@@ -65,7 +66,7 @@ SIGNATURES = {
 # entry points that launch exactly one kernel of ours per successful call
 KERNEL_CALLS = frozenset({
     "jn_gather", "jn_patch_bitmaps", "jn_bitmap_unpack", "jn_split_boxes", "jn_local_boxes", "jn_env_reset",
-    "jn_env_step", "jn_env_props", "jn_env_rewards", "jn_tile_lookup", "jn_returns", "jn_returns_rows", "jn_traj_expand",
+    "jn_env_step", "jn_env_props", "jn_env_rewards", "jn_tile_lookup", "jn_tile_dedupe", "jn_returns", "jn_returns_rows", "jn_traj_expand",
 })
 
 
@@ -139,7 +140,39 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 def stream_ptr(device) -> int:
     """cudaStream_t of torch's current stream on ``device`` -- every launch goes there."""
-    return torch.cuda.current_stream(device).cuda_stream
+    index = device.index if isinstance(device, torch.device) else torch.device(device).index
+    if index is None:
+        index = torch.cuda.current_device()
+    return _raw_stream(index)
+
+
+# the raw-handle accessor skips the construction of a torch.cuda.Stream object (~8 us per call, a few
+# dozen calls per batch); fall back to the public API if a torch release moves it
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None) or (
+    lambda index: torch.cuda.current_stream(index).cuda_stream)
+
+
+class on_device:
+    """``with on_device(dev):`` -- make ``dev`` the current CUDA device for the library calls inside.
+    Unlike ``torch.cuda.device`` it does nothing at all (no context object, no driver call) when ``dev``
+    already is the current device, which is the case in every one-process-per-GPU program."""
+
+    __slots__ = ("index", "guard")
+
+    def __init__(self, device):
+        self.index = device.index
+        self.guard = None
+
+    def __enter__(self):
+        if self.index is not None and torch.cuda.current_device() != self.index:
+            self.guard = torch.cuda.device(self.index)
+            self.guard.__enter__()
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            self.guard.__exit__(*exc)
+            self.guard = None
+        return False
 
 
 def require_cuda(t: torch.Tensor, what: str):

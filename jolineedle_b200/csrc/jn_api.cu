@@ -700,6 +700,19 @@ int jn_tile_lookup(const int64_t* traj_positions, const int32_t* traj_src, int T
   return JN_OK;
 }
 
+int jn_tile_dedupe(const int64_t* traj_positions, const int32_t* traj_src, int n_slots, int T, int32_t* first_src,
+                   int32_t* repeat_src, void* stream) {
+  JN_REQUIRE(T >= 1 && n_slots >= 0 && n_slots % T == 0, "jn_tile_dedupe: n_slots must be a multiple of T");
+  if (n_slots == 0) return JN_OK;
+  JN_REQUIRE(traj_positions && traj_src && first_src && repeat_src, "jn_tile_dedupe: NULL pointer");
+  DeviceInfo dev;
+  if (int rc = current_device_info(dev)) return rc;
+  jnk::tile_dedupe_kernel<<<grid_for(n_slots, 128, dev.sm_count * 8), 128, 0, (cudaStream_t)stream>>>(
+      traj_positions, traj_src, n_slots, T, first_src, repeat_src);
+  JN_CUDA(cudaGetLastError());
+  return JN_OK;
+}
+
 int jn_traj_expand(const int32_t* start_yx, const int32_t* seg_begin, const int32_t* seg_to_yx,
                    const int32_t* seg_tgt_yx, const uint8_t* seg_flags, const int32_t* draw_begin,
                    const uint8_t* draws, const uint32_t* area_bitmaps, int words_per_item, const int32_t* cols, int n,

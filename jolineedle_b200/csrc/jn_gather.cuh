@@ -72,7 +72,7 @@ __device__ __forceinline__ bool decode_chunk(const GatherArgs& a, int q, Chunk& 
   c.src = nullptr;
   c.plane = 0;
   const int img = a.src_index ? a.src_index[c.item] : c.item;
-  if (img < 0) return a.skip_negative != 0;  // zero fill, or skip when the caller asked for that
+  if (img < 0) return a.skip_negative != 0 || img < -1;  // -1: zero fill (or skip on request); <= -2: always skip
   const long long y = a.positions[2 * (long long)c.item], x = a.positions[2 * (long long)c.item + 1];
   const uint8_t* base;
   int h, w;
@@ -322,8 +322,8 @@ __device__ __forceinline__ ChunkPlan plan_chunk(const GatherArgs& a, int q, bool
   const int row0 = (rem - channel * a.chunks_per_plane) * a.rows;
   p.dst = reinterpret_cast<unsigned long long>(a.out + (long long)item * a.out_item_stride);
   p.chrow = (channel << 16) | row0;
-  if (img < 0) {  // zero fill, or skip when the caller asked for that
-    p.flags = a.skip_negative ? kDescSkip : kDescZero;
+  if (img < 0) {  // -1: zero fill (or skip when the caller asked for that); <= -2: always skip
+    p.flags = (a.skip_negative || img < -1) ? kDescSkip : kDescZero;
     return p;
   }
   const long long y = a.positions[2 * (long long)item], x = a.positions[2 * (long long)item + 1];
@@ -502,7 +502,7 @@ gather_rows_kernel(const GatherArgs a, const int out_f32, const int normalize, c
     int h = 0, w = 0;
     long long y = 0, x = 0;
     bool zero_row = img < 0;
-    if (zero_row && a.skip_negative) continue;
+    if (zero_row && (a.skip_negative || img < -1)) continue;
     if (!zero_row) {
       y = a.positions[2 * (long long)item]; x = a.positions[2 * (long long)item + 1];
       if (a.images) {
@@ -571,7 +571,7 @@ __global__ void gather_ldg_kernel(const GatherArgs a, const int out_f32, const i
     const int img = a.src_index ? a.src_index[item] : item;
     float fv = 0.f;
     uint8_t bv = 0;
-    if (img < 0 && a.skip_negative) continue;
+    if (img < 0 && (a.skip_negative || img < -1)) continue;
     if (img >= 0) {
       const long long y = a.positions[2 * (long long)item], x = a.positions[2 * (long long)item + 1];
       const uint8_t* base;

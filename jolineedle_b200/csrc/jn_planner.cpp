@@ -20,7 +20,9 @@
 // fallback for inputs this file does not cover (float boxes, grids wider than 60 patches).
 #include <cmath>
 #include <cstdint>
+#include <algorithm>
 #include <cstring>
+#include <memory>
 #include <random>
 #include <vector>
 
@@ -210,6 +212,33 @@ uint64_t hash_cell(Cell c) {  // tuplehash of a 2-tuple of ints (CPython >= 3.8)
   return acc;
 }
 
+// Bump allocator for the per-episode sets: tables are carved out of a few large blocks and all
+// released at once when the next episode starts (a plan of 256 episodes used to cost ~4000 mallocs).
+struct Arena {
+  std::vector<std::unique_ptr<uint8_t[]>> blocks;
+  std::vector<size_t> sizes;
+  size_t block = 0, off = 0;
+  void reset() { block = 0; off = 0; }
+  void* alloc(size_t bytes) {
+    bytes = (bytes + 15) & ~size_t(15);
+    for (;; ++block, off = 0) {
+      if (block == blocks.size()) {
+        const size_t cap = std::max<size_t>(bytes, size_t(1) << 18);
+        blocks.emplace_back(new uint8_t[cap]);
+        sizes.push_back(cap);
+      }
+      if (off + bytes <= sizes[block]) {
+        void* p = blocks[block].get() + off;
+        off += bytes;
+        return p;
+      }
+    }
+  }
+};
+
+// CPython's set: open addressing, LINEAR_PROBES = 9, perturb shift 5, dummy entries, resize rules of
+// set_add_entry / set_merge.  Tables live in an Arena; copying a PySet aliases its table (copies are
+// only ever read).
 struct PySet {
   enum : uint8_t { kEmpty = 0, kActive = 1, kDummy = 2 };
   struct Entry {
@@ -217,13 +246,19 @@ struct PySet {
     Cell key;
     uint8_t state;
   };
-  std::vector<Entry> table;
+  Arena* arena;
+  Entry* table;
   size_t mask = 7, fill = 0, used = 0;
   static constexpr size_t LP = 9;
 
-  PySet() : table(8, Entry{0, {0, 0}, kEmpty}) {}
+  static Entry* fresh(Arena* a, size_t n) {
+    Entry* t = static_cast<Entry*>(a->alloc(n * sizeof(Entry)));
+    for (size_t i = 0; i < n; ++i) t[i] = Entry{0, {0, 0}, kEmpty};
+    return t;
+  }
+  explicit PySet(Arena* a) : arena(a), table(fresh(a, 8)) {}
 
-  static void insert_clean(std::vector<Entry>& t, size_t mask, Cell key, uint64_t h) {
+  static void insert_clean(Entry* t, size_t mask, Cell key, uint64_t h) {
     size_t perturb = h, i = h & mask;
     for (;;) {
       if (t[i].state == kEmpty) { t[i] = Entry{h, key, kActive}; return; }
@@ -237,13 +272,13 @@ struct PySet {
   void resize(size_t minused) {
     size_t newsize = 8;
     while (newsize <= minused) newsize <<= 1;
-    std::vector<Entry> old;
-    old.swap(table);
-    table.assign(newsize, Entry{0, {0, 0}, kEmpty});
+    const Entry* old = table;
+    const size_t old_size = mask + 1;
+    table = fresh(arena, newsize);
     mask = newsize - 1;
     fill = used;
-    for (const Entry& e : old)
-      if (e.state == kActive) insert_clean(table, mask, e.key, e.hash);
+    for (size_t i = 0; i < old_size; ++i)
+      if (old[i].state == kActive) insert_clean(table, mask, old[i].key, old[i].hash);
   }
   void add(Cell key, uint64_t h) {
     size_t i = h & mask, perturb = h;
@@ -303,7 +338,7 @@ struct PySet {
   }
   // set_merge: `so |= other`, also the body of copying / union
   void merge(const PySet& o) {
-    if (&o == this || o.used == 0) return;
+    if (o.table == table || o.used == 0) return;
     if ((fill + o.used) * 5 >= mask * 3) resize((used + o.used) * 2);
     if (fill == 0 && mask == o.mask && o.fill == o.used) {
       for (size_t i = 0; i <= o.mask; ++i)
@@ -314,8 +349,8 @@ struct PySet {
     }
     if (fill == 0) {
       fill = used = o.used;
-      for (const Entry& e : o.table)
-        if (e.state == kActive) insert_clean(table, mask, e.key, e.hash);
+      for (size_t i = 0; i <= o.mask; ++i)
+        if (o.table[i].state == kActive) insert_clean(table, mask, o.table[i].key, o.table[i].hash);
       return;
     }
     for (size_t i = 0; i <= o.mask; ++i)
@@ -323,8 +358,8 @@ struct PySet {
   }
   template <typename F>
   void for_each(F f) const {
-    for (const Entry& e : table)
-      if (e.state == kActive) f(e.key);
+    for (size_t i = 0; i <= mask; ++i)
+      if (table[i].state == kActive) f(table[i].key);
   }
 };
 
@@ -338,10 +373,10 @@ int64_t pymod(int64_t a, int64_t b) {
 }
 
 // bbox_positions (simple_env.py:270-321), with the reference's set construction sequence
-PySet box_cells(const int64_t* b, int P, int rows, int cols) {
+PySet box_cells(Arena* arena, const int64_t* b, int P, int rows, int cols) {
   const int64_t x1 = b[0], y1 = b[1], x2 = b[2], y2 = b[3];
   const int64_t py_lo = floordiv64(y1, P), py_hi = floordiv64(y2, P), px_lo = floordiv64(x1, P), px_hi = floordiv64(x2, P);
-  PySet cells;
+  PySet cells(arena);
   for (int64_t y = py_lo; y <= py_hi; ++y)
     for (int64_t x = px_lo; x <= px_hi; ++x) {
       const int64_t oh = std::min<int64_t>((y + 1) * P, y2) - std::max<int64_t>(y * P, y1);
@@ -349,9 +384,9 @@ PySet box_cells(const int64_t* b, int P, int rows, int cols) {
       if ((double)(oh * ow) / (double)((int64_t)P * P) > 0.05) cells.add(Cell{(int32_t)y, (int32_t)x});
     }
   cells.add(Cell{(int32_t)floordiv64(floordiv64(y1 + y2, 2), P), (int32_t)floordiv64(floordiv64(x1 + x2, 2), P)});
-  PySet in_x;
+  PySet in_x(arena);
   cells.for_each([&](Cell c) { if (c.x >= 0 && c.x < cols) in_x.add(c); });
-  PySet in_y;
+  PySet in_y(arena);
   in_x.for_each([&](Cell c) { if (c.y >= 0 && c.y < rows) in_y.add(c); });
   return in_y;
 }
@@ -362,6 +397,12 @@ struct jn_plan {
   std::vector<int32_t> start, seg_begin, seg_to, seg_tgt, draw_begin, det_begin, det_yx, final_pos;
   std::vector<uint8_t> seg_flags, draws;
   char error[256] = "";
+  // scratch reused from episode to episode (and from call to call)
+  Arena arena;
+  std::vector<uint8_t> is_box;
+  std::vector<Cell> visited, empties, keypoints, ties;
+  std::vector<int64_t> slots;
+  std::vector<PySet> cells;
 };
 
 namespace {
@@ -371,9 +412,9 @@ struct Episode {
   NumpyRng rng;
   PyRandom& py;
   int rows, cols;
-  std::vector<uint8_t> is_box;  // bbox_patches membership (order never matters for it)
+  std::vector<uint8_t>& is_box;  // bbox_patches membership (order never matters for it)
+  std::vector<Cell>& visited;    // visited_bbox_patches (membership / removal only)
   Cell pos{0, 0};
-  std::vector<Cell> visited;  // visited_bbox_patches (membership / removal only)
 
   bool inside(Cell c) const { return is_box[(size_t)c.y * cols + c.x] != 0; }
   void place(Cell c) {  // reset(position) with visited=None (simple_env.py:335-343)
@@ -419,31 +460,36 @@ int jn_plan_run(jn_plan* plan, int n, const int64_t* boxes, const int32_t* n_box
   o.final_pos.clear();
   o.seg_begin.assign(1, 0); o.draw_begin.assign(1, 0); o.det_begin.assign(1, 0);
   PyRandom py{mt_state, mt_state + 624};
-  std::random_device entropy;
+  std::unique_ptr<std::random_device> entropy;  // only opened for unseeded episodes
   for (int e = 0; e < n; ++e) {
     const int R = rows[e], C = cols[e], nb = max_boxes > 0 ? n_boxes[e] : 0;
     if (R < 1 || C < 1 || R > 60 || C > 60) {
       snprintf(o.error, sizeof(o.error), "episode %d: grid %dx%d outside the native planner's range (binomial inversion needs <= 60)", e, R, C);
       return JN_ERR_UNSUPPORTED;
     }
-    Episode ep{o, NumpyRng(), py, R, C, std::vector<uint8_t>((size_t)R * C, 0)};
+    o.arena.reset();
+    o.is_box.assign((size_t)R * C, 0);
+    o.visited.clear();
+    Episode ep{o, NumpyRng(), py, R, C, o.is_box, o.visited};
     if (has_seed && has_seed[e]) ep.rng.seed_u64(seeds[e]);
     else {
-      uint32_t w[4] = {entropy(), entropy(), entropy(), entropy()};
+      if (!entropy) entropy.reset(new std::random_device());
+      uint32_t w[4] = {(*entropy)(), (*entropy)(), (*entropy)(), (*entropy)()};
       ep.rng.seed(w, 4);
     }
     const int64_t* eb = boxes + (size_t)e * max_boxes * 4;
     // bbox_positions of every box: the reference recomputes them three times (env construction,
     // init_sample, build_keypoints_trajectory); they are pure functions of the box, so once is enough
-    std::vector<PySet> cells;
-    cells.reserve((size_t)nb);
-    for (int k = 0; k < nb; ++k) cells.push_back(box_cells(eb + 4 * k, patch_size, R, C));
+    std::vector<PySet>& cells = o.cells;
+    cells.clear();
+    for (int k = 0; k < nb; ++k) cells.push_back(box_cells(&o.arena, eb + 4 * k, patch_size, R, C));
     // env construction: bbox_patches (membership only)
     for (int k = 0; k < nb; ++k) cells[(size_t)k].for_each([&](Cell c) { ep.is_box[(size_t)c.y * C + c.x] = 1; });
     // init_sample: detection patches = every box patch + one random empty patch, in set order
-    PySet det;
+    PySet det(&o.arena);
     for (int k = 0; k < nb; ++k) cells[(size_t)k].for_each([&](Cell c) { det.add(c); });
-    std::vector<Cell> empties;
+    std::vector<Cell>& empties = o.empties;
+    empties.clear();
     for (int y = 0; y < R; ++y)
       for (int x = 0; x < C; ++x)
         if (!det.contains(Cell{y, x})) empties.push_back(Cell{y, x});
@@ -464,10 +510,11 @@ int jn_plan_run(jn_plan* plan, int n, const int64_t* boxes, const int32_t* n_box
     ep.place(start);
     o.start.push_back(start.y); o.start.push_back(start.x);
     // build_keypoints_trajectory: greedy L1-nearest, ties through random.choice in set order
-    PySet todo;
+    PySet todo(&o.arena);
     for (int k = 0; k < nb; ++k) todo.merge(cells[(size_t)k]);
     for (Cell v : ep.visited) todo.remove(v);
-    std::vector<Cell> keypoints, ties;
+    std::vector<Cell>&keypoints = o.keypoints, &ties = o.ties;
+    keypoints.clear();
     Cell here = ep.pos;
     while (todo.used > 0) {
       long best = -1;
@@ -489,7 +536,8 @@ int jn_plan_run(jn_plan* plan, int n, const int64_t* boxes, const int32_t* n_box
     }
     // random key points: how many, and before which key point
     const int64_t n_random = ep.rng.integers(min_keypoints, (int64_t)max_keypoints + 1);
-    std::vector<int64_t> slots;
+    std::vector<int64_t>& slots = o.slots;
+    slots.clear();
     for (int64_t i = 0; i < n_random; ++i) slots.push_back(ep.rng.integers(0, (int64_t)keypoints.size()));
     for (size_t k = 0; k < keypoints.size(); ++k) {
       const Cell kp = keypoints[k];

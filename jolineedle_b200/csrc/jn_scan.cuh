@@ -77,6 +77,33 @@ __global__ void tile_lookup_kernel(const int64_t* __restrict__ traj_pos, const i
   }
 }
 
+// First occurrences and repeats among the recorded slots of each episode (a walk with detours
+// revisits patches: ~10 % of the slots at BASELINE cfg 2).  Slot k = e*T + t whose patch was already
+// recorded at an earlier slot t' of the same episode gets first_src = -2 (skip) and repeat_src = e*T + t'
+// (the earliest such slot, itself a first occurrence); every other slot keeps its source in first_src
+// (-1 = padded slot, zero-filled) and gets repeat_src = -2.  Two gathers then fill the buffer: first
+// occurrences out of the images, repeats out of the buffer itself -- with host-resident images a
+// revisited tile crosses PCIe once.
+__global__ void tile_dedupe_kernel(const int64_t* __restrict__ traj_pos, const int32_t* __restrict__ traj_src,
+                                   int n_slots, int T, int32_t* __restrict__ first_src,
+                                   int32_t* __restrict__ repeat_src) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_slots; k += gridDim.x * blockDim.x) {
+    const int e = traj_src[k];
+    int first = e, repeat = -2;
+    if (e >= 0) {
+      const long long y = traj_pos[2 * (long long)k], x = traj_pos[2 * (long long)k + 1];
+      const int k0 = k - k % T;
+      for (int j = k0; j < k; ++j)
+        if (traj_src[j] == e && traj_pos[2 * (long long)j] == y && traj_pos[2 * (long long)j + 1] == x) {
+          first = -2; repeat = j;
+          break;
+        }
+    }
+    first_src[k] = first;
+    repeat_src[k] = repeat;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // trajectory expansion (simple_env.py:481-664)
 // ------------------------------------------------------------------------------------------

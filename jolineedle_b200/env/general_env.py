@@ -94,7 +94,7 @@ class NeedleGeneralEnv:
         # K0: patch x bbox containment (any-pixel rule), general_env.py:75,360-379
         self._bbox_words = torch.empty((self.batch_size, self._words), dtype=torch.int32, device=self.device)
         n_boxes = self._boxes_dev.shape[1]
-        with torch.cuda.device(self.device):
+        with _cabi.on_device(self.device):
             _cabi.check(self._lib.jn_patch_bitmaps(
                 self._boxes_dev.data_ptr(), None, self.batch_size, n_boxes, patch_size, self.n_vertical_patches,
                 self.n_horizontal_patches, None, None, _cabi.RULE_ANY_PIXEL, self._bbox_words.data_ptr(),
@@ -111,6 +111,9 @@ class NeedleGeneralEnv:
             ids = torch.arange(self.batch_size * levels, dtype=torch.int32, device=self.device)
             self._level_src = [ids[l::levels].contiguous() for l in range(levels)]  # image b*G + l of level l
         self._t = 0
+        self._launch_gather = None  # bound K1 launch of the one-level step gather (see _gather)
+        self._tile_shape = self._set.out_shape(self.batch_size, focus)
+        self._tile_dtype = self._set.out_dtype(normalize)
         self.init_env_variables()
 
     @torch.no_grad()
@@ -136,7 +139,7 @@ class NeedleGeneralEnv:
     def _unpack(self, words: Tensor) -> Tensor:
         out = torch.empty((self.batch_size, self.n_vertical_patches, self.n_horizontal_patches), dtype=torch.bool,
                           device=self.device)
-        with torch.cuda.device(self.device):
+        with _cabi.on_device(self.device):
             _cabi.check(self._lib.jn_bitmap_unpack(words.data_ptr(), self.batch_size, self.n_vertical_patches,
                                                    self.n_horizontal_patches, out.data_ptr(), self._stream()))
         return out
@@ -173,13 +176,15 @@ class NeedleGeneralEnv:
     def _gather(self) -> Tensor:
         if self.n_glimps_levels > 1:
             return self._gather_levels()
-        out = None
         if self._history is not None:
             out = self._history[:, self._t]
-        patches = self._set.gather(self.positions, out=out, normalize=self._normalize, focus=self._focus,
-                                   engine=self._engine, status=self._status, tag="step", shifts=self._shifts,
-                                   shifts_aligned=self._shifts_aligned)
-        return patches.unsqueeze(1)  # [B, G=1, C, P, P]
+        else:
+            out = torch.empty(self._tile_shape, dtype=self._tile_dtype, device=self.device)
+        if self._launch_gather is None:  # argument checks once per env, not once per step
+            self._launch_gather = self._set.bind(normalize=self._normalize, focus=self._focus, engine=self._engine,
+                                                 status=self._status, tag="step", shifts=self._shifts,
+                                                 shifts_aligned=self._shifts_aligned)
+        return self._launch_gather(self.positions, out).unsqueeze(1)  # [B, G=1, C, P, P]
 
     def _gather_levels(self) -> Tensor:
         """``[B, G, C, P, P]``: the same patch out of every glimpse level (one gather per level; level l of
@@ -217,7 +222,7 @@ class NeedleGeneralEnv:
             torch.stack((ys, xs), dim=1, out=staged)  # pinned staging: the upload does not wait for the stream
             self.positions = staged.to(self.device, non_blocking=True)
         assert tuple(self.positions.shape) == (self.batch_size, 2)
-        with torch.cuda.device(self.device):
+        with _cabi.on_device(self.device):
             _cabi.check(self._lib.jn_env_reset(
                 self.positions.data_ptr(), self._visited_words.data_ptr(), self.steps.data_ptr(),
                 self.has_stopped.data_ptr(), self.batch_size, self.n_vertical_patches, self.n_horizontal_patches,
@@ -225,7 +230,6 @@ class NeedleGeneralEnv:
         infos = {"positions": self.positions}
         return self._gather(), infos
 
-    @torch.no_grad()
     def step(self, actions: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor, dict]:  # general_env.py:172-207
         b, dev = self.batch_size, self.device
         actions = actions.to(device=dev, dtype=torch.long).contiguous()
@@ -234,7 +238,7 @@ class NeedleGeneralEnv:
         rewards = torch.empty((b,), dtype=torch.float32, device=dev)
         terminated = torch.empty((b,), dtype=torch.bool, device=dev)
         truncated = torch.empty((b,), dtype=torch.bool, device=dev)
-        with torch.cuda.device(dev):
+        with _cabi.on_device(dev):
             _cabi.check(self._lib.jn_env_step(
                 self.positions.data_ptr(), actions.data_ptr(), new_positions.data_ptr(),
                 self._visited_words.data_ptr(), self._bbox_words.data_ptr(), self.steps.data_ptr(),
@@ -250,7 +254,7 @@ class NeedleGeneralEnv:
     def _props(self, want_prop: bool, want_term: bool):
         prop = torch.empty((self.batch_size,), dtype=torch.float32, device=self.device) if want_prop else None
         term = torch.empty((self.batch_size,), dtype=torch.bool, device=self.device) if want_term else None
-        with torch.cuda.device(self.device):
+        with _cabi.on_device(self.device):
             _cabi.check(self._lib.jn_env_props(
                 self._visited_words.data_ptr(), self._bbox_words.data_ptr(), self.has_stopped.data_ptr(),
                 self.batch_size, self.n_vertical_patches, self.n_horizontal_patches, 1 if self.stop_enabled else 0,
@@ -274,7 +278,7 @@ class NeedleGeneralEnv:
         """Reward of the CURRENT state (general_env.py:321-358).  ``step`` evaluates it between the move and
         the visited-map update; called on its own it sees whatever the visited map holds now."""
         out = torch.empty((self.batch_size,), dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
+        with _cabi.on_device(self.device):
             _cabi.check(self._lib.jn_env_rewards(
                 self.positions.data_ptr(), self._visited_words.data_ptr(), self._bbox_words.data_ptr(),
                 self.has_stopped.data_ptr(), self.batch_size, self.n_vertical_patches, self.n_horizontal_patches,
@@ -288,7 +292,7 @@ class NeedleGeneralEnv:
         b = boxes.shape[0]
         words = torch.empty((b, self._words), dtype=torch.int32, device=self.device)
         out = torch.empty((b, self.n_vertical_patches, self.n_horizontal_patches), dtype=torch.bool, device=self.device)
-        with torch.cuda.device(self.device):
+        with _cabi.on_device(self.device):
             _cabi.check(self._lib.jn_patch_bitmaps(
                 boxes.data_ptr(), None, b, boxes.shape[1], self.patch_size, self.n_vertical_patches,
                 self.n_horizontal_patches, None, None, _cabi.RULE_ANY_PIXEL, words.data_ptr(), self._words,
@@ -330,7 +334,7 @@ class NeedleGeneralEnv:
         rows, cols = self.n_vertical_patches, self.n_horizontal_patches
         local = torch.empty((b, rows, cols, n, 4), dtype=torch.long, device=self.device)
         present = torch.empty((b, rows, cols, n), dtype=torch.bool, device=self.device)
-        with torch.cuda.device(self.device):
+        with _cabi.on_device(self.device):
             _cabi.check(self._lib.jn_split_boxes(boxes.data_ptr(), b, n, self.patch_size, rows, cols,
                                                  local.data_ptr(), present.data_ptr(), self._status.data_ptr(),
                                                  self._stream()))

@@ -230,7 +230,7 @@ def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normaliz
     }
     gather_src = torch.empty((n, T), dtype=torch.int32, device=dev)
     ep_len = torch.empty((n,), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with _cabi.on_device(dev):
         # K0: 5 %-area bitmaps (labels = inside_bbox, simple_env.py:225,478)
         _cabi.check(lib.jn_patch_bitmaps(d_boxes.data_ptr(), d_nboxes.data_ptr(), n, p.boxes.shape[1], P, 0, 0,
                                          d_rows.data_ptr(), d_cols.data_ptr(), _cabi.RULE_AREA5, area.data_ptr(),
@@ -248,9 +248,26 @@ def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normaliz
                                            out["positions"].data_ptr(), gather_src.data_ptr(), n * T,
                                            out["local_bboxes"].data_ptr(), stream))
     # K1: the glimpses themselves, straight into [B, T, C, P, P]; padded slots are zero-filled
-    image_set.gather(out["positions"].view(n * T, 2), src_index=gather_src.view(n * T),
-                     out=out["patches"].view((n * T,) + out["patches"].shape[2:]), normalize=normalize,
-                     engine=engine, status=status, tag="trajectory")
+    traj_tiles = out["patches"].view((n * T,) + out["patches"].shape[2:])
+    reuse_set = None
+    if image_set.host_mapped and reuse_glimpses:
+        # Host-resident images: a walk with detours revisits patches (~10 % of the slots); those tiles are
+        # copied inside HBM from their first occurrence instead of crossing PCIe again.  The trajectory
+        # buffer doubles as a set of n*T one-patch images for that (and for the detection patches below).
+        reuse_set = ImageSet(traj_tiles, P)
+        first_src = torch.empty((n * T,), dtype=torch.int32, device=dev)
+        repeat_src = torch.empty((n * T,), dtype=torch.int32, device=dev)
+        with _cabi.on_device(dev):
+            _cabi.check(lib.jn_tile_dedupe(out["positions"].data_ptr(), gather_src.data_ptr(), n * T, T,
+                                           first_src.data_ptr(), repeat_src.data_ptr(), stream))
+        image_set.gather(out["positions"].view(n * T, 2), src_index=first_src, out=traj_tiles, normalize=normalize,
+                         engine=engine, status=status, tag="trajectory")
+        reuse_set.gather(torch.zeros((n * T, 2), dtype=torch.long, device=dev), src_index=repeat_src, out=traj_tiles,
+                         engine=engine, status=status, tag="trajectory-reuse")
+        out["_host_traj_tiles"] = (first_src >= 0).sum()  # trajectory tiles that did cross PCIe
+    else:
+        image_set.gather(out["positions"].view(n * T, 2), src_index=gather_src.view(n * T), out=traj_tiles,
+                         normalize=normalize, engine=engine, status=status, tag="trajectory")
     # detection patches: every box patch + one random empty patch per image (simple_env.py:397-441)
     # (the number of detection patches varies from batch to batch, and a buffer of a new size is a fresh
     # multi-GB cudaMalloc -- tens of milliseconds -- for torch's caching allocator.  So the capacity only
@@ -262,35 +279,22 @@ def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normaliz
     if need > det_cap:
         det_cap = _det_capacity[key] = -(-(need + need // 8) // 64) * 64
     det_buf = torch.empty(image_set.out_shape(det_cap, False), dtype=torch.float32, device=dev)
-    if image_set.host_mapped and reuse_glimpses and n_det > 0:
+    if reuse_set is not None and n_det > 0:
         # Host-resident images: most detection patches were just gathered as trajectory glimpses, so take
-        # those from the [n*T, C, P, P] buffer in HBM instead of pulling them over PCIe a second time.  The
-        # buffer joins the image set as one more slab of n*T one-patch images.
-        traj_tiles = out["patches"].view((n * T,) + out["patches"].shape[2:])
-        if normalize:
-            # uint8 host images but float32 glimpses: two passes over the same output, each leaving the other's
-            # items untouched (skip_negative): normalising gather of the host tiles, plain copy of the reused ones
-            reuse_set = ImageSet(traj_tiles, P)
-            pos2 = torch.empty((n_det, 2), dtype=torch.long, device=dev)
-            src2 = torch.empty((n_det,), dtype=torch.int32, device=dev)
-            with torch.cuda.device(dev):
-                _cabi.check(lib.jn_tile_lookup(out["positions"].data_ptr(), gather_src.data_ptr(), T,
-                                               d_det_pos.data_ptr(), d_det_src.data_ptr(), n_det, image_set.n_images,
-                                               pos2.data_ptr(), src2.data_ptr(), stream))
-            minus_one, n_img = torch.full_like(src2, -1), image_set.n_images
-            image_set.gather(pos2, src_index=torch.where(src2 < n_img, src2, minus_one), out=det_buf[:n_det],
-                             normalize=True, engine=engine, status=status, tag="detection", skip_negative=True)
-            reuse_set.gather(pos2, src_index=torch.where(src2 >= n_img, src2 - n_img, minus_one), out=det_buf[:n_det],
-                             engine=engine, status=status, tag="detection-reuse", skip_negative=True)
-        else:
-            joint = ImageSet(list(image_set._slabs) + [traj_tiles], P, device=dev)
-            pos2 = torch.empty((n_det, 2), dtype=torch.long, device=dev)
-            src2 = torch.empty((n_det,), dtype=torch.int32, device=dev)
-            with torch.cuda.device(dev):
-                _cabi.check(lib.jn_tile_lookup(out["positions"].data_ptr(), gather_src.data_ptr(), T,
-                                               d_det_pos.data_ptr(), d_det_src.data_ptr(), n_det, image_set.n_images,
-                                               pos2.data_ptr(), src2.data_ptr(), stream))
-            joint.gather(pos2, src_index=src2, out=det_buf[:n_det], engine=engine, status=status, tag="detection")
+        # those from the [n*T, C, P, P] buffer in HBM instead of pulling them over PCIe a second time: two
+        # passes over the same output, each leaving the other's items untouched (skip_negative) -- gather of
+        # the host tiles (normalising when the images are uint8), plain copy of the reused ones.
+        pos2 = torch.empty((n_det, 2), dtype=torch.long, device=dev)
+        src2 = torch.empty((n_det,), dtype=torch.int32, device=dev)
+        with _cabi.on_device(dev):
+            _cabi.check(lib.jn_tile_lookup(out["positions"].data_ptr(), gather_src.data_ptr(), T,
+                                           d_det_pos.data_ptr(), d_det_src.data_ptr(), n_det, image_set.n_images,
+                                           pos2.data_ptr(), src2.data_ptr(), stream))
+        minus_one, n_img = torch.full_like(src2, -1), image_set.n_images
+        image_set.gather(pos2, src_index=torch.where(src2 < n_img, src2, minus_one), out=det_buf[:n_det],
+                         normalize=normalize, engine=engine, status=status, tag="detection", skip_negative=True)
+        reuse_set.gather(pos2, src_index=torch.where(src2 >= n_img, src2 - n_img, minus_one), out=det_buf[:n_det],
+                         engine=engine, status=status, tag="detection-reuse", skip_negative=True)
         out["patches_yolox"] = det_buf[:n_det]
         out["_host_det_tiles"] = (src2 < image_set.n_images).sum()  # detection tiles that did cross PCIe
     else:
@@ -298,7 +302,7 @@ def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normaliz
                                                 normalize=normalize, engine=engine, status=status, tag="detection")
     det_boxes = torch.empty((n_det, n_max, 6), dtype=torch.float32, device=dev)
     if n_max > 0 and n_det > 0:
-        with torch.cuda.device(dev):
+        with _cabi.on_device(dev):
             _cabi.check(lib.jn_local_boxes(d_boxes.data_ptr(), d_nboxes.data_ptr(), n_max, P, d_det_pos.data_ptr(),
                                            d_det_src.data_ptr(), n_det, det_boxes.data_ptr(), stream))
     out["bboxes_yolox"] = det_boxes

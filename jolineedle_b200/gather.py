@@ -33,16 +33,16 @@ class ImageSet:
         if any(len(sh) not in (3, 4) for sh in shapes):
             bad = next(sh for sh in shapes if len(sh) not in (3, 4))
             raise ValueError(f"images must be [C,H,W] or [B,C,H,W], got shape {tuple(bad)}")
-        on_gpu = [t.is_cuda for t in slabs]
-        self.host_mapped = not all(on_gpu)
+        where = [t.get_device() for t in slabs]  # CUDA device index, -1 for host tensors
+        self.host_mapped = min(where) < 0
         if self.host_mapped:
-            for t, g in zip(slabs, on_gpu):
-                if not g and (device is None or not t.is_pinned()):
+            for t, d in zip(slabs, where):
+                if d < 0 and (device is None or not t.is_pinned()):
                     _cabi.require_cuda(t, "images")
-        devices = {t.device for t, g in zip(slabs, on_gpu) if g}
+        devices = {d for d in where if d >= 0}
         if len(devices) > 1 or any(t.dtype != dtype for t in slabs) or any(sh[-3] != channels for sh in shapes):
             raise ValueError("all images of a set must share device, dtype and channel count")
-        cuda_device = next(iter(devices)) if devices else None
+        cuda_device = torch.device("cuda", next(iter(devices))) if devices else None
         norm = [t if t.is_contiguous() else t.contiguous() for t in slabs]
         counts = [sh[0] if len(sh) == 4 else 1 for sh in shapes]
         heights, widths = [sh[-2] for sh in shapes], [sh[-1] for sh in shapes]
@@ -70,7 +70,7 @@ class ImageSet:
         handle = ctypes.c_void_p()
         a_ptrs = np.array(ptrs, dtype=np.uint64)
         a_dims = np.array([counts, heights, widths], dtype=np.int32)  # rows are contiguous int32 arrays
-        with torch.cuda.device(self.device):
+        with _cabi.on_device(self.device):
             rc = _cabi.lib().jn_images_create(
                 ctypes.byref(handle), n, a_ptrs.ctypes.data, a_dims[0].ctypes.data, a_dims[1].ctypes.data,
                 a_dims[2].ctypes.data, channels,
@@ -100,6 +100,43 @@ class ImageSet:
 
     def out_dtype(self, normalize: bool) -> torch.dtype:
         return torch.float32 if normalize else self.dtype
+
+    def bind(self, normalize: bool = False, focus: bool = False, engine: str = "auto",
+             status: Optional[torch.Tensor] = None, tag: str = "", shifts: Optional[torch.Tensor] = None,
+             shifts_aligned: bool = False):
+        """``launch(positions, out)`` for a fixed gather configuration, with the argument checks of
+        :meth:`gather` done once: the batched env calls it every step with its own, known-good tensors
+        (``positions`` a contiguous int64 ``[n, 2]`` on this device, ``out`` with contiguous items of the
+        right shape and dtype, item i of image i)."""
+        if shifts is not None and (shifts.dtype != torch.int32 or tuple(shifts.shape) != (self.n_images, 2)
+                                   or shifts.device != self.device or not shifts.is_contiguous()):
+            raise ValueError(f"shifts must be a contiguous int32 [{self.n_images}, 2] tensor of (ty, tx) on {self.device}")
+        flags = (_cabi.GATHER_NORMALIZE if normalize else 0) | (_cabi.GATHER_FOCUS if focus else 0)
+        if shifts is not None and shifts_aligned:
+            flags |= _cabi.GATHER_SHIFT_ALIGNED
+        lib, handle, code = _cabi.lib(), self._handle, _cabi.ENGINES[engine]
+        p_status, p_shifts, device = _cabi.ptr(status), _cabi.ptr(shifts), self.device
+        keep = (status, shifts, self)  # the raw pointers above stay valid as long as the closure lives
+
+        def launch(positions: torch.Tensor, out: torch.Tensor):
+            n = positions.shape[0]
+            stride = (out.stride(0) if n > 1 else out[0].numel()) * out.element_size()
+            timing = TIMING
+            with _cabi.on_device(device):
+                if timing is not None:
+                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ev0.record()
+                rc = lib.jn_gather(handle, positions.data_ptr(), None, p_shifts, n, out.data_ptr(), stride, flags, code,
+                                   p_status, _cabi.stream_ptr(device))
+                if timing is not None:
+                    ev1.record()
+                    timing.append((tag, n, ev0, ev1))
+            if rc:
+                _cabi.check(rc)
+            return out
+
+        launch.keep = keep
+        return launch
 
     def gather(
         self,
@@ -147,7 +184,7 @@ class ImageSet:
             flags |= _cabi.GATHER_SKIP_NEGATIVE
         stride = out.stride(0) * out.element_size() if n > 1 else out[0].numel() * out.element_size() if n else 0
         timing = TIMING
-        with torch.cuda.device(self.device):
+        with _cabi.on_device(self.device):
             if timing is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()

@@ -29,7 +29,7 @@ def compute_returns(rewards: Tensor, logit_masks: Tensor) -> Tensor:
         lm = lm.contiguous()
     b, t = rewards.shape
     out = torch.empty((b, t), dtype=torch.float32, device=rewards.device)
-    with torch.cuda.device(rewards.device):
+    with _cabi.on_device(rewards.device):
         _cabi.check(_cabi.lib().jn_returns_rows(rewards.data_ptr(), rewards.stride(0), lm.data_ptr(), lm.stride(0),
                                                 t, b, out.data_ptr(), _cabi.stream_ptr(rewards.device)))
     return out
@@ -48,7 +48,7 @@ def rollout_tail(rewards_tn: Tensor, terminated_tn: Tensor) -> Dict[str, Tensor]
     masks = torch.empty((b, t + 1), dtype=torch.bool, device=dev)
     logit_masks = torch.empty((b, t), dtype=torch.bool, device=dev)
     returns = torch.empty((b, t), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _cabi.on_device(dev):
         _cabi.check(_cabi.lib().jn_returns(rewards_tn.data_ptr(), terminated_tn.data_ptr(), t, b, rewards.data_ptr(),
                                            masks.data_ptr(), logit_masks.data_ptr(), returns.data_ptr(),
                                            _cabi.stream_ptr(dev)))

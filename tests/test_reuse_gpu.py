@@ -48,7 +48,28 @@ def test_detection_patches_reuse_trajectory_glimpses(src):
     n_det = want["patches_yolox"].shape[0]
     from_host = int(stats["host_det_tiles"])
     assert 0 < from_host < n_det, (from_host, n_det)  # at least the empty patches come from the host, box patches mostly not
+    # trajectory slots that revisit a patch of their episode are copied inside HBM, not re-read from the host
+    recorded = int(want["masks"].sum())
+    pos, m = want["positions"].cpu().numpy(), want["masks"].cpu().numpy()
+    distinct = sum(len({tuple(pos[i, t]) for t in range(T) if m[i, t] > 0}) for i in range(b))
+    assert int(stats["host_traj_tiles"]) == distinct and distinct < recorded, (distinct, recorded)
     assert int(stats["status"].item()) == 0
+
+
+def test_tile_dedupe_marks_first_occurrences_and_repeats():
+    from jolineedle_b200 import _cabi
+
+    T = 5
+    #            episode 0: A B A (pad) (pad)      episode 1: C C D C D
+    pos = torch.tensor([[1, 1], [1, 2], [1, 1], [0, 0], [0, 0], [2, 0], [2, 0], [0, 3], [2, 0], [0, 3]], dtype=torch.int64)
+    src = torch.tensor([0, 0, 0, -1, -1, 1, 1, 1, 1, 1], dtype=torch.int32)
+    first = torch.empty(10, dtype=torch.int32, device="cuda")
+    repeat = torch.empty(10, dtype=torch.int32, device="cuda")
+    p, s_ = pos.cuda(), src.cuda()
+    _cabi.check(_cabi.lib().jn_tile_dedupe(p.data_ptr(), s_.data_ptr(), 10, T, first.data_ptr(), repeat.data_ptr(),
+                                           _cabi.stream_ptr(p.device)))
+    assert first.tolist() == [0, 0, -2, -1, -1, 1, -2, 1, -2, -2]
+    assert repeat.tolist() == [-2, -2, 0, -2, -2, -2, 5, -2, 5, 7]
 
 
 def test_skip_negative_leaves_tiles_untouched():
@@ -66,3 +87,15 @@ def test_skip_negative_leaves_tiles_untouched():
         assert bool((out[1] == 7).all()) and bool((out[3] == 7).all()), engine
         s.gather(pos, src_index=src, out=out, engine=engine)  # default: negative = zero fill
         assert float(out[1].abs().sum()) == 0.0 and float(out[3].abs().sum()) == 0.0
+        # -1 = zero fill, JN_SRC_SKIP (-2) = always left untouched, also without the flag
+        out.fill_(7.0)
+        s.gather(pos, src_index=torch.tensor([2, -2, -1, -2], dtype=torch.int32).cuda(), out=out, engine=engine)
+        assert bool((out[1] == 7).all()) and bool((out[3] == 7).all()) and float(out[2].abs().sum()) == 0.0, engine
+    u8 = ImageSet(torch.from_numpy(synth_u8(3, 3, 2 * P, 3 * P, salt=1)).cuda(), P)
+    for engine in ("tensor", "bulk", "ldg"):  # the same through the converting kernel
+        for focus in (False, True):
+            out = torch.full(u8.out_shape(4, focus), 7.0, device="cuda")
+            u8.gather(pos, src_index=torch.tensor([2, -2, -1, -2], dtype=torch.int32).cuda(), out=out, engine=engine,
+                      normalize=True, focus=focus)
+            assert bool((out[1] == 7).all()) and bool((out[3] == 7).all()) and float(out[2].abs().sum()) == 0.0
+            assert float(out[0].sum()) > 0

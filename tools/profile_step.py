@@ -1,11 +1,15 @@
-"""Host-side profile of one supervised bench step (cProfile + phase timers with syncs)."""
+"""Host-side profile of one bench step (cProfile + phase timers with syncs).
+    python tools/profile_step.py [supervised|reinforce|aerial] [u8|f32] [batch]"""
 import cProfile, pstats, sys, os, time, io
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
-src = sys.argv[1] if len(sys.argv) > 1 else "f32"
+workload = sys.argv[1] if len(sys.argv) > 1 else "supervised"
+src = sys.argv[2] if len(sys.argv) > 2 else "u8"
 dev = torch.device("cuda", 0)
-wl = bench.SupervisedWorkload(256, 0, dev, src)
+cls, default_batch = bench.WORKLOADS[workload]
+batch = int(sys.argv[3]) if len(sys.argv) > 3 else default_batch
+wl = cls(batch, 0, dev, src if workload == "supervised" else "u8")
 wl.to_device()
 for s in range(3):
     wl.run(s)
@@ -18,4 +22,5 @@ for s in range(6, 11):
     wl.run(s)
 torch.cuda.synchronize()
 pr.disable()
-st = io.StringIO(); pstats.Stats(pr, stream=st).sort_stats("cumtime").print_stats(28); print(st.getvalue()[:6000])
+st = io.StringIO(); pstats.Stats(pr, stream=st).sort_stats("cumtime").print_stats(34); print(st.getvalue()[:8000])
+st = io.StringIO(); pstats.Stats(pr, stream=st).sort_stats("tottime").print_stats(20); print(st.getvalue()[:5000])
