@@ -360,6 +360,7 @@ def main():
                     help="distinct pinned host images per rank in the e2e arm (default: all of them up to 2 ranks, "
                          "64 beyond, to bound page-locked host memory at 8 ranks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-timing", action="store_true", help="also time every gather of the e2e arm (diagnostics)")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi (A/B of the sampler's own cost)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -453,6 +454,10 @@ def main():
     for tag, n_items, e0, e1 in timing:
         by_tag.setdefault(tag, []).append(e0.elapsed_time(e1))
     gather_ms = {tag: round(sum(v) / len(v), 4) for tag, v in by_tag.items()}  # mean launch time of every gather
+    items_by_tag = {}
+    for tag, n_items, e0, e1 in timing:
+        items_by_tag.setdefault(tag, []).append(n_items)
+    gather_items = {tag: round(sum(v) / len(v), 1) for tag, v in items_by_tag.items()}
     # DRAM traffic per launch of that kernel from the committed `ncu --set full` capture of this workload at its
     # default batch (profiles/r01/ncu_summary.json, produced by tools/gpu_ci.sh ncu); null when there is none
     traffic, traffic_src = None, None
@@ -489,9 +494,7 @@ def main():
         full = sum(t.numel() * t.element_size() for t in host) if isinstance(host, list) else host.numel() * host.element_size()
         zero_copy = args.workload == "supervised"  # pinned lists are gathered in place; batched RL images are uploaded
         wl_patch = getattr(wl, "PATCH", P)
-        e2e_steps = max(2, min(args.steps, 5))
-        wl.run(0, images=host, device=device)
-        barrier()
+        e2e_steps = max(2, min(args.steps, 10))
         eunits, d2h_bytes, h2d = 0.0, 0, 0
         side = torch.cuda.Stream(device)
         tile_bytes = 3 * wl_patch * wl_patch * (1 if src == "u8" else 4)
@@ -527,23 +530,40 @@ def main():
                 eunits += float(wl.batch * (wl.T + 1))
                 h2d += full
 
+        def pipeline(first_step, n_steps):
+            pending = None
+            for s in range(n_steps):
+                nxt = launch(first_step + s)
+                if pending is not None:
+                    finish(pending)
+                pending = nxt
+            finish(pending)
+            torch.cuda.current_stream(device).wait_stream(side)
+
+        # warm-up runs the timed loop verbatim: pinned read-back buffers, the side stream's allocator pool and
+        # the zero-copy path's scratch all exist before the clock starts (a cudaHostAlloc or cudaMalloc inside a
+        # 0.2 s window would halve the figure)
+        pipeline(0, 3)
+        barrier()
+        eunits, d2h_bytes, h2d = 0.0, 0, 0
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gather.TIMING = [] if args.e2e_timing else None
         t0.record()
-        pending = None
-        for s in range(e2e_steps):
-            nxt = launch(args.warmup + s)
-            if pending is not None:
-                finish(pending)
-            pending = nxt
-        finish(pending)
-        torch.cuda.current_stream(device).wait_stream(side)
+        pipeline(args.warmup, e2e_steps)
         t1.record()
         barrier()
         ems = max_over_ranks(t0.elapsed_time(t1), device)
+        e2e_tags = {}
+        for tag, n_items, ev_a, ev_b in (gather.TIMING or []):
+            e2e_tags.setdefault(tag, []).append((n_items, ev_a.elapsed_time(ev_b)))
+        gather.TIMING = None
         how = ("read in place by the gather kernels (zero-copy over PCIe: only glimpsed tiles move)" if zero_copy
                else "uploaded inside the timed region")
         e2e = {"value": sum_over_ranks(eunits, device) / (ems / 1e3), "unit": "gaze-steps/s",
                "h2d_bytes_per_step": int(h2d / e2e_steps), "d2h_bytes_per_step": int(d2h_bytes), "steps": e2e_steps,
+               **({"gather_by_tag": {k: {"items": round(sum(n for n, _ in v) / len(v), 1),
+                                          "ms": round(sum(m for _, m in v) / len(v), 3)} for k, v in e2e_tags.items()}}
+                  if e2e_tags else {}),
                "host_buffers": f"pinned {src} images ({full} bytes addressed on the host"
                                + (f", {len(distinct)} distinct" if zero_copy else "") + f"), {how}"}
         del host
@@ -576,6 +596,7 @@ def main():
                        "parallelism": f"episodes sharded over {world} GPU(s), no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks.summary(), "host_ms_per_step": host_ms, "gather_ms_by_tag": gather_ms,
+            "gather_items_by_tag": gather_items,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

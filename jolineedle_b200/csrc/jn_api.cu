@@ -427,9 +427,10 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
     if (!tma_mode || !out_aligned || !set->bulk_ok) engine = JN_ENGINE_LDG;
     else if (shifts) engine = (shift_copy_ok || shift_xform_ok) ? JN_ENGINE_TENSOR : JN_ENGINE_LDG;
     else {
-      // uint8 -> fp32 tiles of 256 < P < 1024: per-row bulk copies measured 1-2 % faster than tensor tiles
-      // (two boxes per row); everywhere else the engines tie or the tensor tiles win
-      const bool prefer_bulk = normalize && P > 256 && P < 1024;
+      // tiles wider than one TMA box (P > 256: two or more boxes per row): per-row bulk copies measured 1-7 %
+      // faster than tensor tiles in every mode (profiles/r01/micro_quick_v2.jsonl); up to 256 the engines tie
+      // or the tensor tiles win
+      const bool prefer_bulk = set->kbox > 1;
       engine = (set->tensor_ok && set->n_slabs == 1 && !prefer_bulk) ? JN_ENGINE_TENSOR : JN_ENGINE_BULK;
     }
   }

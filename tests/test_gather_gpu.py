@@ -203,3 +203,34 @@ def test_zero_copy_gather_from_pinned_host_memory(engine, dtype):
 
     with pytest.raises(_cabi.NativeLibraryError):
         ImageSet(imgs.clone(), P, device="cuda")
+
+
+def test_converting_gather_back_to_back_and_on_two_streams():
+    """The converting kernel claims its chunks from a global counter that it leaves at zero for the next
+    launch; launches rotate through a pool of counters so that two streams never share one.  Many launches
+    of different sizes back to back, then interleaved on two streams, must all be exact."""
+    from jolineedle_b200.gather import ImageSet
+
+    P, gh, gw, b = 64, 4, 5, 6
+    imgs = make_images(b, gh * P, gw * P, torch.uint8, salt=3)
+    s = ImageSet(imgs.cuda(), P)
+    rng = np.random.default_rng(11)
+    cases = []
+    for n in (1, 3, 17, 64, 257, 1024, 5, 2048, 2):
+        pos = torch.from_numpy(np.stack([rng.integers(0, gh, n), rng.integers(0, gw, n)], 1).astype(np.int64))
+        src = torch.from_numpy(rng.integers(-1, b, n).astype(np.int32))
+        focus = bool(n % 2)
+        cases.append((pos.cuda(), src.cuda(), focus, ref_gather(list(imgs), pos, src, P, True, focus)))
+    outs = [s.gather(p, src_index=k, normalize=True, focus=f) for (p, k, f, _) in cases for _ in range(3)]
+    torch.cuda.synchronize()
+    for i, o in enumerate(outs):
+        assert torch.equal(o.cpu(), cases[i // 3][3]), i
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = []
+    for rep in range(4):
+        for i, (p, k, f, _) in enumerate(cases):
+            with torch.cuda.stream(streams[(i + rep) % 2]):
+                outs.append((i, s.gather(p, src_index=k, normalize=True, focus=f)))
+    torch.cuda.synchronize()
+    for i, o in outs:
+        assert torch.equal(o.cpu(), cases[i][3]), i
