@@ -84,7 +84,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "250", "-i",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
                  str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -172,6 +172,11 @@ class SupervisedWorkload:
     def gaze_steps(self, out):
         return out["masks"].sum()  # recorded glimpses (padded slots are not glimpses)
 
+    def host_tiles(self, out, stats):
+        """Tiles that crossed PCIe: first occurrences of trajectory slots + detection patches no glimpse held."""
+        zero = torch.zeros((), dtype=torch.long, device=out["masks"].device)
+        return stats.get("host_traj_tiles", zero) + stats.get("host_det_tiles", zero)
+
     def gather_bytes(self, n_items, valid_items, tag):
         s_in = 1 if self.src_dtype == "u8" else 4
         tile = 3 * P * P
@@ -248,7 +253,7 @@ class ReinforceWorkload:
         imgs = self.images if images is None else images
         env = NeedleGeneralEnv(imgs, self.boxes, self.PATCH, self.T, 1, stop_enabled=True,
                                normalize=(self.src_dtype == "u8"), history=True, device=device,
-                               translate=self.translate)
+                               translate=self.translate, zero_copy=images is not None)
         # (seeds the CPU generator reset() draws its start positions from; torch.manual_seed would also walk
         # through every accelerator backend, 0.1 ms a call)
         torch.default_generator.manual_seed(step * 31 + self.rank)
@@ -264,7 +269,11 @@ class ReinforceWorkload:
         rewards, term = torch.stack(rewards), torch.stack(term)  # [T, B] as the trainer collects them
         out = rollout_tail(rewards, term)
         out["positions"] = env.positions
+        out["host_tiles"] = env.host_tiles  # tiles read over PCIe (zero-copy env only)
         return out
+
+    def host_tiles(self, out, stats):
+        return out["host_tiles"]
 
     def gaze_steps(self, out):
         return torch.tensor(float(self.batch * (self.T + 1)), device=self.device)
@@ -345,7 +354,7 @@ def reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="supervised", choices=sorted(WORKLOADS))
@@ -492,7 +501,7 @@ def main():
         else:
             host = pinned(wl.images)
         full = sum(t.numel() * t.element_size() for t in host) if isinstance(host, list) else host.numel() * host.element_size()
-        zero_copy = args.workload == "supervised"  # pinned lists are gathered in place; batched RL images are uploaded
+        zero_copy = True  # pinned images are gathered in place (supervised lists and the batched RL env alike)
         wl_patch = getattr(wl, "PATCH", P)
         e2e_steps = max(2, min(args.steps, 10))
         eunits, d2h_bytes, h2d = 0.0, 0, 0
@@ -509,26 +518,20 @@ def main():
             with torch.cuda.stream(side):
                 side.wait_event(done)
                 hostres, nbytes = wl.d2h(out, non_blocking=True)
-                counts = None
-                if zero_copy:  # tiles that crossed PCIe: first occurrences of trajectory slots + unseen detection patches
-                    zero = torch.zeros((), dtype=torch.long, device=device)
-                    tiles = torch.stack([stats.get("host_traj_tiles", zero), stats.get("host_det_tiles", zero)])
-                    counts = read_back({"tiles": tiles}, True)[0]["tiles"]
+                counts = read_back({"tiles": wl.host_tiles(out, stats).reshape(1)}, True)[0]["tiles"]
                 read = torch.cuda.Event()
                 read.record(side)
-            return out, hostres, nbytes, counts, read
+            # `out` and `stats` were allocated on the launch stream and are read on the side stream: both stay
+            # referenced until finish() so that the allocator cannot hand their memory to the next step early
+            return (out, stats), hostres, nbytes, counts, read
 
         def finish(pending):
             nonlocal eunits, d2h_bytes, h2d
             out, hostres, nbytes, counts, read = pending
             read.synchronize()  # the step's results are on the host
             d2h_bytes = nbytes
-            if zero_copy:
-                eunits += float(hostres["masks"].sum())
-                h2d += float(counts.sum()) * tile_bytes
-            else:
-                eunits += float(wl.batch * (wl.T + 1))
-                h2d += full
+            eunits += float(hostres["masks"].sum()) if args.workload == "supervised" else float(wl.batch * (wl.T + 1))
+            h2d += float(counts.sum()) * tile_bytes
 
         def pipeline(first_step, n_steps):
             pending = None
@@ -557,15 +560,14 @@ def main():
         for tag, n_items, ev_a, ev_b in (gather.TIMING or []):
             e2e_tags.setdefault(tag, []).append((n_items, ev_a.elapsed_time(ev_b)))
         gather.TIMING = None
-        how = ("read in place by the gather kernels (zero-copy over PCIe: only glimpsed tiles move)" if zero_copy
-               else "uploaded inside the timed region")
+        how = "read in place by the gather kernels (zero-copy over PCIe: only glimpsed tiles move, each once)"
         e2e = {"value": sum_over_ranks(eunits, device) / (ems / 1e3), "unit": "gaze-steps/s",
                "h2d_bytes_per_step": int(h2d / e2e_steps), "d2h_bytes_per_step": int(d2h_bytes), "steps": e2e_steps,
                **({"gather_by_tag": {k: {"items": round(sum(n for n, _ in v) / len(v), 1),
                                           "ms": round(sum(m for _, m in v) / len(v), 3)} for k, v in e2e_tags.items()}}
                   if e2e_tags else {}),
                "host_buffers": f"pinned {src} images ({full} bytes addressed on the host"
-                               + (f", {len(distinct)} distinct" if zero_copy else "") + f"), {how}"}
+                               + (f", {len(distinct)} distinct" if isinstance(host, list) else "") + f"), {how}"}
         del host
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ------------------------------------------------

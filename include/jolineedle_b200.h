@@ -186,6 +186,17 @@ int jn_env_props(const uint32_t* visited, const uint32_t* bbox, const uint8_t* h
                  int rows, int cols, int stop_enabled, float* prop_patches, uint8_t* terminated,
                  void* stream);
 
+/* Where this step's glimpse of every episode comes from when the images live in pinned HOST memory and the
+ * crops are kept in a [n, slots, C, P, P] history buffer (NeedleGeneralEnv(history=True), the in-place form
+ * of the trainer's concat, reinforce.py:175-179): first_slot int32 [n, rows*cols] (-1 = patch never seen)
+ * records the history slot that first held each patch of each episode.  For the current positions
+ * (int64 [n, 2]) and the slot `t` about to be written: a patch seen for the first time gets
+ * host_src[i] = i, history_src[i] = JN_SRC_SKIP and is recorded; a revisited patch gets host_src[i] =
+ * JN_SRC_SKIP and history_src[i] = i * slots + first_slot (the history as a set of one-patch images).
+ * Two gathers then fill slot t; a patch crosses PCIe once per episode. */
+int jn_visit_sources(const int64_t* positions, int32_t* first_slot, int n, int rows, int cols, int slots,
+                     int t, int32_t* host_src, int32_t* history_src, int32_t* status, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K3  segmented scans.
  * ------------------------------------------------------------------------------------------ */

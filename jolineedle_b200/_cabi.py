@@ -55,6 +55,7 @@ SIGNATURES = {
                                _P, _P, _P]),
     "jn_tile_lookup": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, _P, _P, _P]),
     "jn_tile_dedupe": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
+    "jn_visit_sources": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "jn_plan_create": (c_int, [POINTER(_P)]),
     "jn_plan_destroy": (None, [_P]),
     "jn_plan_error": (c_char_p, [_P]),
@@ -66,7 +67,7 @@ SIGNATURES = {
 # entry points that launch exactly one kernel of ours per successful call
 KERNEL_CALLS = frozenset({
     "jn_gather", "jn_patch_bitmaps", "jn_bitmap_unpack", "jn_split_boxes", "jn_local_boxes", "jn_env_reset",
-    "jn_env_step", "jn_env_props", "jn_env_rewards", "jn_tile_lookup", "jn_tile_dedupe", "jn_returns", "jn_returns_rows", "jn_traj_expand",
+    "jn_env_step", "jn_env_props", "jn_env_rewards", "jn_tile_lookup", "jn_tile_dedupe", "jn_visit_sources", "jn_returns", "jn_returns_rows", "jn_traj_expand",
 })
 
 

@@ -701,6 +701,20 @@ int jn_tile_lookup(const int64_t* traj_positions, const int32_t* traj_src, int T
   return JN_OK;
 }
 
+int jn_visit_sources(const int64_t* positions, int32_t* first_slot, int n, int rows, int cols, int slots, int t,
+                     int32_t* host_src, int32_t* history_src, int32_t* status, void* stream) {
+  JN_REQUIRE(n >= 0 && rows >= 1 && cols >= 1 && slots >= 1 && t >= 0 && t < slots, "jn_visit_sources: bad sizes");
+  JN_REQUIRE((long long)n * slots < (1ll << 31), "jn_visit_sources: history of %d x %d slots is too large", n, slots);
+  if (n == 0) return JN_OK;
+  JN_REQUIRE(positions && first_slot && host_src && history_src, "jn_visit_sources: NULL pointer");
+  DeviceInfo dev;
+  if (int rc = current_device_info(dev)) return rc;
+  jnk::visit_sources_kernel<<<grid_for(n, 128, dev.sm_count * 8), 128, 0, (cudaStream_t)stream>>>(
+      positions, first_slot, n, rows, cols, slots, t, host_src, history_src, status);
+  JN_CUDA(cudaGetLastError());
+  return JN_OK;
+}
+
 int jn_tile_dedupe(const int64_t* traj_positions, const int32_t* traj_src, int n_slots, int T, int32_t* first_src,
                    int32_t* repeat_src, void* stream) {
   JN_REQUIRE(T >= 1 && n_slots >= 0 && n_slots % T == 0, "jn_tile_dedupe: n_slots must be a multiple of T");

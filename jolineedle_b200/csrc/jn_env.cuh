@@ -315,4 +315,29 @@ __global__ void env_props_kernel(const uint32_t* __restrict__ visited, const uin
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// first-visit table of the zero-copy env (host-resident images + crop history)
+// ------------------------------------------------------------------------------------------
+// One thread per episode: has this episode seen its current patch before, and in which history slot?
+__global__ void visit_sources_kernel(const int64_t* __restrict__ positions, int32_t* __restrict__ first_slot, int n,
+                                     int rows, int cols, int slots, int t, int32_t* __restrict__ host_src,
+                                     int32_t* __restrict__ history_src, int32_t* __restrict__ status) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const long long y = positions[2 * (long long)i], x = positions[2 * (long long)i + 1];
+    if (y < 0 || x < 0 || y >= rows || x >= cols) {
+      if (status) atomicOr(status, 1);  // out-of-grid position: the gather skips it too
+      host_src[i] = -2; history_src[i] = -2;
+      continue;
+    }
+    int32_t* cell = first_slot + (long long)i * rows * cols + y * cols + x;
+    const int seen = *cell;
+    if (seen < 0) {
+      *cell = t;
+      host_src[i] = i; history_src[i] = -2;
+    } else {
+      host_src[i] = -2; history_src[i] = i * slots + seen;
+    }
+  }
+}
+
 }  // namespace jnk

@@ -46,6 +46,7 @@ class NeedleGeneralEnv:
         engine: str = "auto",
         device=None,
         translate: Optional[Tensor] = None,
+        zero_copy: bool = False,
     ):
         # same preconditions as general_env.py:37-39,50-51
         assert images.shape[0] == bboxes.shape[0]
@@ -53,9 +54,18 @@ class NeedleGeneralEnv:
         assert n_glimps_levels > 0
         if n_glimps_levels != 1 and (translate is not None or images.dtype != torch.float32):
             raise NotImplementedError("the glimpse pyramid (n_glimps_levels > 1) needs float32 images and no translate")
-        if device is not None and not images.is_cuda:
+        # zero_copy: pinned HOST images are not uploaded -- every step's gather reads the glimpsed tiles in place
+        # over PCIe, and with history=True a patch an episode has already seen is copied from the crop history in
+        # HBM instead (jn_visit_sources), so each patch crosses PCIe at most once per episode
+        self._zero_copy = bool(zero_copy and device is not None and not images.is_cuda and images.is_pinned())
+        if zero_copy and not self._zero_copy and not images.is_cuda:
+            raise ValueError("zero_copy needs pinned host images and device=")
+        if self._zero_copy and n_glimps_levels != 1:
+            raise NotImplementedError("zero_copy serves one glimpse level")
+        if device is not None and not images.is_cuda and not self._zero_copy:
             images = images.to(device, non_blocking=True)
-        _cabi.require_cuda(images, "images")
+        if not self._zero_copy:
+            _cabi.require_cuda(images, "images")
         self.patch_size = patch_size
         self.max_ep_len = max_ep_len
         self.n_glimps_levels = n_glimps_levels
@@ -65,7 +75,9 @@ class NeedleGeneralEnv:
         assert self.width % self.patch_size == 0
         self.n_vertical_patches = self.height // self.patch_size
         self.n_horizontal_patches = self.width // self.patch_size
-        self.device = images.device
+        self.device = torch.device(device) if self._zero_copy else images.device
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self._normalize, self._focus, self._engine = normalize, focus, engine
         self._shifts, self._shifts_aligned = None, False
         if translate is not None:
@@ -77,7 +89,7 @@ class NeedleGeneralEnv:
             self._shifts = t.to(torch.int32).flip(1).contiguous().to(self.device)
 
         if n_glimps_levels == 1:
-            self._set = ImageSet(images, patch_size)
+            self._set = ImageSet(images, patch_size, device=self.device if self._zero_copy else None)
             # [B, G=1, C, H, W] view of the caller's tensor (callers read env.images[0, 0]); the reflect-pad +
             # resize the reference computes and throws away at one level (general_env.py:95-111) is not done
             self.images = self._set._slabs[0].unsqueeze(1)
@@ -106,6 +118,13 @@ class NeedleGeneralEnv:
             self._history = torch.empty(
                 (self.batch_size, (max_ep_len + 1) * n_glimps_levels) + self._set.out_shape(1, focus)[1:],
                 dtype=self._set.out_dtype(normalize), device=self.device)
+        self._history_set = None
+        if self._zero_copy and self._history is not None:
+            slots = self._history.shape[1]
+            self._history_set = ImageSet(self._history.view((self.batch_size * slots,) + tuple(self._history.shape[2:])),
+                                         self._history.shape[-1])  # one-patch images (P, or P/2 in the Focus layout)
+            self._origin = torch.zeros((self.batch_size, 2), dtype=torch.long, device=self.device)
+        self.host_tiles = torch.zeros((), dtype=torch.long, device=self.device)  # tiles read over PCIe so far
         if n_glimps_levels > 1:
             levels = n_glimps_levels
             ids = torch.arange(self.batch_size * levels, dtype=torch.int32, device=self.device)
@@ -160,6 +179,9 @@ class NeedleGeneralEnv:
         self.steps = torch.zeros((b,), dtype=torch.long, device=dev)
         self.has_stopped = torch.zeros((b,), dtype=torch.bool, device=dev)
         self._t = 0
+        if getattr(self, "_history_set", None) is not None:
+            self._first_slot = torch.full((b, self.n_vertical_patches * self.n_horizontal_patches), -1,
+                                          dtype=torch.int32, device=dev)
 
     def check_status(self):
         """Synchronise and raise if a kernel flagged invalid input (the reference raises at the
@@ -180,11 +202,32 @@ class NeedleGeneralEnv:
             out = self._history[:, self._t]
         else:
             out = torch.empty(self._tile_shape, dtype=self._tile_dtype, device=self.device)
+        if self._history_set is not None:
+            return self._gather_zero_copy(out).unsqueeze(1)
         if self._launch_gather is None:  # argument checks once per env, not once per step
             self._launch_gather = self._set.bind(normalize=self._normalize, focus=self._focus, engine=self._engine,
                                                  status=self._status, tag="step", shifts=self._shifts,
                                                  shifts_aligned=self._shifts_aligned)
         return self._launch_gather(self.positions, out).unsqueeze(1)  # [B, G=1, C, P, P]
+
+    def _gather_zero_copy(self, out: Tensor) -> Tensor:
+        """Slot ``t`` of the history from pinned host images: patches seen for the first time come over PCIe,
+        revisited ones are copied from the slot that first held them."""
+        b, dev = self.batch_size, self.device
+        host_src = torch.empty((b,), dtype=torch.int32, device=dev)
+        hist_src = torch.empty((b,), dtype=torch.int32, device=dev)
+        with _cabi.on_device(dev):
+            _cabi.check(self._lib.jn_visit_sources(
+                self.positions.data_ptr(), self._first_slot.data_ptr(), b, self.n_vertical_patches,
+                self.n_horizontal_patches, self._history.shape[1], self._t, host_src.data_ptr(), hist_src.data_ptr(),
+                self._status.data_ptr(), self._stream()))
+        self._set.gather(self.positions, src_index=host_src, out=out, normalize=self._normalize, focus=self._focus,
+                         engine=self._engine, status=self._status, tag="step", shifts=self._shifts,
+                         shifts_aligned=self._shifts_aligned)
+        self._history_set.gather(self._origin, src_index=hist_src, out=out, engine=self._engine, status=self._status,
+                                 tag="step-reuse")
+        self.host_tiles += (host_src >= 0).sum()
+        return out
 
     def _gather_levels(self) -> Tensor:
         """``[B, G, C, P, P]``: the same patch out of every glimpse level (one gather per level; level l of
