@@ -10,6 +10,7 @@ rm -f gpurun_out/summary.txt
 note() { echo "$@" | tee -a gpurun_out/summary.txt; }
 
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv,noheader > gpurun_out/gpu.txt 2>&1
+{ nvidia-smi topo -m; lscpu | grep -iE "model name|socket|numa|^cpu\(s\)"; python -c "import os; print('affinity', sorted(os.sched_getaffinity(0)))"; free -g | head -2; } > gpurun_out/topo.txt 2>&1
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; note "smoke rc=$?"
 timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/pytest_gpu.log 2>&1
 note "pytest_gpu rc=$? $(tail -1 gpurun_out/pytest_gpu.log)"
@@ -39,5 +40,9 @@ if [ "$1" = "ncu" ]; then
   $CMD > gpurun_out/plain_rl.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:"env_step|gather_xform" -s 130 -c 4 -o gpurun_out/prof_rl $CMD > gpurun_out/ncu_rl.log 2>&1
   note "ncu reinforce rc=$?"
+  CMD="python bench.py --workload aerial --steps 1 --warmup 3 --batch 64 --no-e2e --no-cpu-baseline"
+  $CMD > gpurun_out/plain_aerial.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:"env_step|gather_xform" -s 200 -c 4 -o gpurun_out/prof_aerial $CMD > gpurun_out/ncu_aerial.log 2>&1
+  note "ncu aerial rc=$?"
 fi
 cat gpurun_out/summary.txt
