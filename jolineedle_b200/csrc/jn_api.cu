@@ -625,10 +625,19 @@ int jn_env_step(const int64_t* pos_in, const int64_t* actions, int64_t* pos_out,
     JN_CUDA(cudaGetLastError());
     return JN_OK;
   }
-  const int wpb = 4;
-  jnk::env_step_kernel<<<grid_for(n, wpb, dev.sm_count * 16), wpb * 32, 0, (cudaStream_t)stream>>>(
-      pos_in, actions, pos_out, visited, bbox, steps, has_stopped, rewards, terminated, truncated, n, rows, cols,
-      jn_bitmap_words(rows, cols), max_ep_len, cost, stop_enabled, status);
+  // groups of G lanes per episode, G = the power of two >= the number of bitmap words (at most a warp)
+  const int words = jn_bitmap_words(rows, cols), wpb = 4;
+  int g = 1;
+  while (g < words && g < 32) g <<= 1;
+  const int per_block = wpb * (32 / g);
+#define JN_STEP(G)                                                                                               \
+  case G:                                                                                                        \
+    jnk::env_step_group_kernel<G><<<grid_for(n, per_block, dev.sm_count * 16), wpb * 32, 0, (cudaStream_t)stream>>>( \
+        pos_in, actions, pos_out, visited, bbox, steps, has_stopped, rewards, terminated, truncated, n, rows, cols, \
+        words, max_ep_len, cost, stop_enabled, status);                                                          \
+    break;
+  switch (g) { JN_STEP(1) JN_STEP(2) JN_STEP(4) JN_STEP(8) JN_STEP(16) JN_STEP(32) }
+#undef JN_STEP
   JN_CUDA(cudaGetLastError());
   return JN_OK;
 }

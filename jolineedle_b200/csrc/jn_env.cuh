@@ -168,58 +168,71 @@ __global__ void env_reset_kernel(const int64_t* __restrict__ positions, uint32_t
   }
 }
 
-__global__ void env_step_kernel(const int64_t* __restrict__ pos_in, const int64_t* __restrict__ actions,
-                                int64_t* __restrict__ pos_out, uint32_t* __restrict__ visited,
-                                const uint32_t* __restrict__ bbox, int64_t* __restrict__ steps,
-                                uint8_t* __restrict__ has_stopped, float* __restrict__ rewards,
-                                uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, int n, int rows,
-                                int cols, int words, int max_ep_len, float cost, int stop_enabled,
-                                int32_t* __restrict__ status) {
+// A group of G lanes (G = the power of two >= the number of bitmap words, at most 32) owns an episode:
+// lane k of the group owns words k, k+G, ...; a warp steps 32/G episodes at once (32x32 grid: 32 words, one
+// warp per episode; 8x8 grid: 2 words, 16 episodes per warp).  Counts are reduced inside the group with
+// xor-shuffles.  Every lane of a group computes the scalar tail (same values, uniform instructions) and lane 0
+// of the group stores, so that no instruction runs with a single active lane.
+template <int G>
+__global__ void env_step_group_kernel(const int64_t* __restrict__ pos_in, const int64_t* __restrict__ actions,
+                                      int64_t* __restrict__ pos_out, uint32_t* __restrict__ visited,
+                                      const uint32_t* __restrict__ bbox, int64_t* __restrict__ steps,
+                                      uint8_t* __restrict__ has_stopped, float* __restrict__ rewards,
+                                      uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, int n,
+                                      int rows, int cols, int words, int max_ep_len, float cost, int stop_enabled,
+                                      int32_t* __restrict__ status) {
+  constexpr int kPerWarp = 32 / G;
   const int warps_per_block = blockDim.x >> 5;
-  const int lane = threadIdx.x & 31;
-  for (int e = blockIdx.x * warps_per_block + (threadIdx.x >> 5); e < n; e += gridDim.x * warps_per_block) {
-    // --- move + clamp, sticky stop (general_env.py:209-233); all lanes compute the same scalars
-    long long a = actions[e];
-    if (a < 0 || a > kStop) {
-      if (lane == 0 && status) atomicOr(status, 2);
-      a = kStop;  // invalid code: no move (flagged); the reference raises ValueError here
-    }
-    long long y = pos_in[2 * (long long)e] + kActionDy[a];
-    long long x = pos_in[2 * (long long)e + 1] + kActionDx[a];
+  const int lane = threadIdx.x & 31, sub = lane & (G - 1), group = lane / G;
+  const int stride = gridDim.x * warps_per_block * kPerWarp;
+  for (int base = (blockIdx.x * warps_per_block + (threadIdx.x >> 5)) * kPerWarp; base < n; base += stride) {
+    const int e = base + group;
+    const bool live = e < n;  // lanes past the end still take part in the shuffles
+    // --- move + clamp, sticky stop (general_env.py:209-233)
+    const long long a_raw = live ? actions[e] : (long long)kStop;
+    const bool bad_action = a_raw < 0 || a_raw > kStop;
+    if (bad_action && sub == 0 && status) atomicOr(status, 2);
+    const long long a = bad_action ? (long long)kStop : a_raw;  // invalid code: no move (flagged); the reference raises
+    long long y = (live ? pos_in[2 * (long long)e] : 0) + kActionDy[a];
+    long long x = (live ? pos_in[2 * (long long)e + 1] : 0) + kActionDx[a];
     y = lmin(lmax(y, 0), rows - 1);
     x = lmin(lmax(x, 0), cols - 1);
-    const bool stopped = (has_stopped[e] != 0) || (a == kStop && actions[e] == kStop);
+    const bool stopped = live && ((has_stopped[e] != 0) || a_raw == kStop);
     const int bit = (int)(y * cols + x);
-    // --- bitmaps: lane l owns words l, l+32, ...
-    int found = 0, every = 0, missing_after = 0;
-    bool fresh_here = false;
-    for (int w = lane; w < words; w += 32) {
-      const uint32_t v = visited[(long long)e * words + w];
-      const uint32_t b = bbox[(long long)e * words + w];
-      found += __popc(v & b);  // counts use the map BEFORE marking (general_env.py:347)
-      every += __popc(b);
-      uint32_t v_new = v;
-      if ((bit >> 5) == w) {
-        const uint32_t m = 1u << (bit & 31);
-        fresh_here = (b & m) != 0 && (v & m) == 0;
-        v_new = v | m;
-        visited[(long long)e * words + w] = v_new;
+    // --- bitmaps
+    int found = 0, every = 0, missing_after = 0, fresh = 0;
+    if (live) {
+      for (int w = sub; w < words; w += G) {
+        const uint32_t v = visited[(long long)e * words + w];
+        const uint32_t b = bbox[(long long)e * words + w];
+        found += __popc(v & b);  // counts use the map BEFORE marking (general_env.py:347)
+        every += __popc(b);
+        uint32_t v_new = v;
+        if ((bit >> 5) == w) {
+          const uint32_t m = 1u << (bit & 31);
+          fresh = ((b & m) != 0 && (v & m) == 0) ? 1 : 0;
+          v_new = v | m;
+          visited[(long long)e * words + w] = v_new;
+        }
+        missing_after += __popc(b & ~v_new);
       }
-      missing_after += __popc(b & ~v_new);
     }
-    found = warp_sum(found);
-    every = warp_sum(every);
-    missing_after = warp_sum(missing_after);
-    const bool fresh = __any_sync(kFullMask, fresh_here);
-    if (lane == 0) {
-      // reward = fl32(fl32(fresh + cost) + stop_eval), general_env.py:334-358
-      float r = __fadd_rn(fresh ? 1.0f : 0.0f, cost);
-      if (stop_enabled) {
-        const int stop_eval = stopped ? (found == every ? found : found - every) : 0;
-        r = __fadd_rn(r, (float)stop_eval);
-      }
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) {
+      found += __shfl_xor_sync(kFullMask, found, off);
+      every += __shfl_xor_sync(kFullMask, every, off);
+      missing_after += __shfl_xor_sync(kFullMask, missing_after, off);
+      fresh |= __shfl_xor_sync(kFullMask, fresh, off);
+    }
+    // --- reward = fl32(fl32(fresh + cost) + stop_eval), general_env.py:334-358
+    float r = __fadd_rn(fresh ? 1.0f : 0.0f, cost);
+    if (stop_enabled) {
+      const int stop_eval = stopped ? (found == every ? found : found - every) : 0;
+      r = __fadd_rn(r, (float)stop_eval);
+    }
+    const long long s = (live ? steps[e] : 0) + 1;
+    if (live && sub == 0) {
       rewards[e] = r;
-      const long long s = steps[e] + 1;
       steps[e] = s;
       has_stopped[e] = stopped ? 1 : 0;
       truncated[e] = s >= max_ep_len ? 1 : 0;
@@ -232,8 +245,8 @@ __global__ void env_step_kernel(const int64_t* __restrict__ pos_in, const int64_
 
 // Single-word grids (rows*cols <= 32, e.g. the 5x6 LARD grid of cfg 2/3): the whole bitmap of an
 // episode is one register, so a *lane* owns an episode and a warp steps 32 of them with every lane
-// busy (the warp-per-episode kernel above would idle 31 lanes in its bitmap loop and its scalar
-// tail).  Same arithmetic, same order of operations.
+// busy with 16-byte position loads and stores.  Same arithmetic, same order of operations as the group
+// kernel above (whose G = 1 instance serves one-word grids with unaligned position buffers).
 __global__ void env_step_lane_kernel(const int64_t* __restrict__ pos_in, const int64_t* __restrict__ actions,
                                      int64_t* __restrict__ pos_out, uint32_t* __restrict__ visited,
                                      const uint32_t* __restrict__ bbox, int64_t* __restrict__ steps,
