@@ -99,6 +99,15 @@ int jn_images_create(jn_images** out, int n_slabs, const void* const* slab_ptrs 
  * synchronises).  With both NULL the library allocates and uploads the table itself
  * (cudaMalloc / cudaFree synchronise the device). */
 static inline int64_t jn_images_table_bytes(int64_t n_images) { return n_images * 32; }
+/* Same, for images whose height / width are NOT multiples of patch_size: the set behaves as if every
+ * image had been zero-padded at the bottom / right up to the next multiple (complete_to_patch_size and
+ * padded_collate_fn, dataset.py:307-347,379-406) -- the patch grid is ceil(H/P) x ceil(W/P) and the pixels
+ * of the edge tiles that lie outside the image are zeros -- without materialising the padding (the TMA unit
+ * zero-fills out-of-bounds bytes; sets the tensor engine cannot address fall back to plain loads). */
+int jn_images_create_padded(jn_images** out, int n_slabs, const void* const* slab_ptrs /*HOST*/,
+                            const int32_t* counts /*HOST*/, const int32_t* heights /*HOST*/,
+                            const int32_t* widths /*HOST*/, int channels, int dtype /*jn_dtype*/,
+                            int patch_size, void* table_host /*HOST*/, void* table_dev, void* stream);
 void jn_images_destroy(jn_images* set);
 /* 1 if the TMA engines can serve this set (16-byte aligned bases / rows / patches), else 0. */
 int jn_images_tma_ok(const jn_images* set, int engine /*jn_engine*/);
@@ -121,9 +130,10 @@ int jn_images_tma_ok(const jn_images* set, int engine /*jn_engine*/);
  * image translated by (tx, ty) pixels with zero fill -- tile pixel (r, c) of patch (y, x) is image
  * pixel (y*P + r - ty, x*P + c - tx) -- i.e. the integer `translate` augmentation of the reference's
  * dataset (dataset.py:157-226, torchvision F.affine with fill 0) folded into the gather instead of
- * materialising a shifted copy of the image.  Served by a plain-load kernel (one warp per tile row);
- * the TMA unit only accepts inner offsets that are 16-byte multiples, so it is used when the caller
- * sets JN_GATHER_SHIFT_ALIGNED (one slab, P <= 256).
+ * materialising a shifted copy of the image.  One slab: any offset rides the TMA engine (the unit only
+ * accepts inner offsets that are 16-byte multiples, so the converting kernel loads the aligned superset of
+ * every row and realigns it in shared memory; same-dtype uint8 copies need JN_GATHER_SHIFT_ALIGNED and
+ * P <= 256).  Lists of images: plain-load kernel (one warp per tile row).
  *
  * `status` (device int32[1], may be NULL) is OR-ed with 1 if some position was outside the
  * patch grid (that tile is skipped).

@@ -37,6 +37,7 @@ SIGNATURES = {
     "jn_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "jn_selftest_host": (c_int, [POINTER(c_float), POINTER(c_int)]),
     "jn_images_create": (c_int, [POINTER(_P), c_int, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
+    "jn_images_create_padded": (c_int, [POINTER(_P), c_int, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
     "jn_images_destroy": (None, [_P]),
     "jn_images_tma_ok": (c_int, [_P, c_int]),
     "jn_gather": (c_int, [_P, _P, _P, _P, c_int, _P, c_int64, c_uint32, c_int, _P, _P]),

@@ -118,6 +118,7 @@ struct jn_images {
   // several slabs
   jnk::ImageRec* d_recs = nullptr;
   bool owns_recs = true;
+  bool padded = false;  // sizes are rounded up to the patch grid; pixels outside the image read as zeros
   // engines
   bool bulk_ok = false, tensor_ok = false;
   int box_w = 0, kbox = 0;
@@ -293,9 +294,9 @@ int jn_selftest_host(float* unit_out /*HOST [256]*/, int* direction_out /*HOST [
 // ------------------------------------------------------------------------------------------
 // image sets
 // ------------------------------------------------------------------------------------------
-int jn_images_create(jn_images** out, int n_slabs, const void* const* slab_ptrs, const int32_t* counts,
-                     const int32_t* heights, const int32_t* widths, int channels, int dtype, int patch_size,
-                     void* table_host, void* table_dev, void* stream) {
+static int images_create(jn_images** out, int n_slabs, const void* const* slab_ptrs, const int32_t* counts,
+                         const int32_t* heights, const int32_t* widths, int channels, int dtype, int patch_size,
+                         void* table_host, void* table_dev, void* stream, bool padded) {
   JN_REQUIRE(out != nullptr, "jn_images_create: out is NULL");
   *out = nullptr;
   JN_REQUIRE(n_slabs >= 1 && slab_ptrs && counts && heights && widths, "jn_images_create: empty image set");
@@ -307,7 +308,8 @@ int jn_images_create(jn_images** out, int n_slabs, const void* const* slab_ptrs,
   for (int k = 0; k < n_slabs; ++k) {
     JN_REQUIRE(slab_ptrs[k] != nullptr && counts[k] >= 1, "jn_images_create: slab %d is empty", k);
     // same precondition as the reference envs (general_env.py:50-51, simple_env.py:68-69)
-    JN_REQUIRE(heights[k] > 0 && widths[k] > 0 && heights[k] % patch_size == 0 && widths[k] % patch_size == 0,
+    JN_REQUIRE(heights[k] > 0 && widths[k] > 0 &&
+                   (padded || (heights[k] % patch_size == 0 && widths[k] % patch_size == 0)),
                "image size %dx%d is not a multiple of patch_size %d", heights[k], widths[k], patch_size);
     total += counts[k];
     aligned = aligned && (reinterpret_cast<uintptr_t>(slab_ptrs[k]) % 16 == 0) && ((long long)widths[k] * elem) % 16 == 0;
@@ -317,6 +319,7 @@ int jn_images_create(jn_images** out, int n_slabs, const void* const* slab_ptrs,
   jn_images* s = new jn_images();
   s->n_slabs = n_slabs; s->n_images = (int)total; s->channels = channels; s->dtype = dtype; s->elem = elem;
   s->patch = patch_size;
+  s->padded = padded;
   cudaGetDevice(&s->device);
   s->bulk_ok = aligned;
   s->box_w = aligned ? pick_box_width(patch_size, elem) : 0;
@@ -357,6 +360,20 @@ int jn_images_create(jn_images** out, int n_slabs, const void* const* slab_ptrs,
   }
   *out = s;
   return JN_OK;
+}
+
+int jn_images_create(jn_images** out, int n_slabs, const void* const* slab_ptrs, const int32_t* counts,
+                     const int32_t* heights, const int32_t* widths, int channels, int dtype, int patch_size,
+                     void* table_host, void* table_dev, void* stream) {
+  return images_create(out, n_slabs, slab_ptrs, counts, heights, widths, channels, dtype, patch_size, table_host,
+                       table_dev, stream, false);
+}
+
+int jn_images_create_padded(jn_images** out, int n_slabs, const void* const* slab_ptrs, const int32_t* counts,
+                            const int32_t* heights, const int32_t* widths, int channels, int dtype, int patch_size,
+                            void* table_host, void* table_dev, void* stream) {
+  return images_create(out, n_slabs, slab_ptrs, counts, heights, widths, channels, dtype, patch_size, table_host,
+                       table_dev, stream, true);
 }
 
 void jn_images_destroy(jn_images* s) {
@@ -405,6 +422,7 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
   a.channels = C; a.height = set->height; a.width = set->width; a.patch = P; a.elem = set->elem;
   a.box_w = set->box_w; a.kbox = set->kbox;
   a.skip_negative = (flags & JN_GATHER_SKIP_NEGATIVE) ? 1 : 0;
+  a.padded = set->padded ? 1 : 0;
 
   const bool plain_copy = !normalize && !focus;
   const bool out_aligned = reinterpret_cast<uintptr_t>(out) % 16 == 0 && out_item_stride_bytes % 16 == 0;
@@ -418,14 +436,16 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
   //    kernel's superset loads: any x offset (the TMA unit itself traps on inner coordinates that are not
   //    16-byte multiples), rows of up to 2032 bytes;
   //  * the rest (lists of images, uint8 -> uint8, wider rows) is served by the plain-load engine.
+  // Padded sets (sizes that are not multiples of the patch) need the same out-of-image zero fill: they ride the
+  // superset loads as well, translated or not.
   const bool shift_copy_ok = plain_copy && set->tensor_ok && set->n_slabs == 1 && set->kbox == 1 &&
-                             (flags & JN_GATHER_SHIFT_ALIGNED) != 0;
+                             (flags & JN_GATHER_SHIFT_ALIGNED) != 0 && !set->padded;
   const int shift_pitch = P * set->elem + 16;
   const bool shift_xform_ok = set->tensor_ok && set->n_slabs == 1 && shift_pitch / 8 <= 256 && P >= 8 &&
                               (normalize || set->dtype == JN_F32);
   if (engine == JN_ENGINE_AUTO) {
     if (!tma_mode || !out_aligned || !set->bulk_ok) engine = JN_ENGINE_LDG;
-    else if (shifts) engine = (shift_copy_ok || shift_xform_ok) ? JN_ENGINE_TENSOR : JN_ENGINE_LDG;
+    else if (shifts || set->padded) engine = (shift_copy_ok || shift_xform_ok) ? JN_ENGINE_TENSOR : JN_ENGINE_LDG;
     else {
       // tiles wider than one TMA box (P > 256: two or more boxes per row): per-row bulk copies measured 1-7 %
       // faster than tensor tiles in every mode (profiles/r01/micro_quick_v2.jsonl); up to 256 the engines tie
@@ -434,19 +454,19 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
       engine = (set->tensor_ok && set->n_slabs == 1 && !prefer_bulk) ? JN_ENGINE_TENSOR : JN_ENGINE_BULK;
     }
   }
-  if (shifts && engine == JN_ENGINE_TENSOR)
+  if ((shifts || set->padded) && engine == JN_ENGINE_TENSOR)
     JN_REQUIRE(shift_copy_ok || shift_xform_ok,
                "translated gathers on the tensor engine need one slab and tile rows of at most 2032 bytes "
                "(uint8 -> uint8 copies: patch_size <= 256 and JN_GATHER_SHIFT_ALIGNED)");
-  if (shifts && engine == JN_ENGINE_BULK)
-    return fail(JN_ERR_INVALID, "the bulk engine cannot translate (needs 16-byte aligned row starts); use auto");
+  if ((shifts || set->padded) && engine == JN_ENGINE_BULK)
+    return fail(JN_ERR_INVALID, "the bulk engine cannot translate or pad (no zero fill outside the image); use auto");
   if (engine == JN_ENGINE_TENSOR)
     JN_REQUIRE(tma_mode && out_aligned && set->tensor_ok && set->n_slabs == 1,
                "tensor-map engine unavailable for this image set / flags (needs one slab, 16-byte aligned rows)");
   if (engine == JN_ENGINE_BULK)
     JN_REQUIRE(tma_mode && out_aligned && set->bulk_ok, "bulk engine needs 16-byte aligned bases, rows and patches");
   // translated gathers on the xform kernel (superset loads) -- also plain float32 copies that are not vouched for
-  const bool shift_xform = shifts != nullptr && engine == JN_ENGINE_TENSOR && !shift_copy_ok;
+  const bool shift_xform = (shifts != nullptr || set->padded) && engine == JN_ENGINE_TENSOR && !shift_copy_ok;
 
   if (engine == JN_ENGINE_LDG) {
     a.rows = 1; a.chunks_per_plane = P; a.total_chunks = 0;

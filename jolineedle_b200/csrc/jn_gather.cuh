@@ -50,6 +50,7 @@ struct GatherArgs {
   int pitch, stage_bytes;       // xform kernel: bytes per staged row (patch * elem, + 16 when translating), per stage
   uint32_t wpr_magic;           // xform kernel: ceil(2^32 / (patch / 4)), division by multiply-high
   int* work_counter;            // xform kernel: {next unclaimed chunk, CTAs done}; zero before and after a launch
+  int padded;                   // image sizes are rounded up to the patch grid, pixels outside the image are zeros
   int skip_negative;            // negative src_index: 1 = leave the output tile untouched, 0 = zero-fill it
 };
 
@@ -60,6 +61,11 @@ struct Chunk {
   int plane, px, py;  // plane = index of (image, channel) inside the slab: the tensor map's outer coordinate
   int sy, sx;  // translation of the source image: tile pixel (r, c) <- image pixel (py*P + r - sy, px*P + c - sx)
 };
+
+// Extent of the patch grid in pixels: the image size, rounded up to whole patches for padded sets.
+__device__ __forceinline__ int grid_extent(const GatherArgs& a, int size) {
+  return a.padded ? (size + a.patch - 1) / a.patch * a.patch : size;
+}
 
 // Decode chunk q.  Out-of-grid positions are reported once and treated as "skip" (src = null,
 // skip = true); negative src_index means zero fill (src = null, skip = false).
@@ -337,7 +343,8 @@ __device__ __forceinline__ ChunkPlan plan_chunk(const GatherArgs& a, int q, bool
     base = a.base + (long long)img * a.image_stride; h = a.height; w = a.width;
     p.plane = img * a.channels + channel;
   }
-  if (img >= a.n_images || y < 0 || x < 0 || (y + 1) * a.patch > h || (x + 1) * a.patch > w) {
+  if (img >= a.n_images || y < 0 || x < 0 || (y + 1) * a.patch > grid_extent(a, h) ||
+      (x + 1) * a.patch > grid_extent(a, w)) {
     if (a.status && channel == 0 && row0 == 0) atomicOr(a.status, 1);
     return p;  // out-of-grid position: reported once, tile skipped
   }
@@ -511,7 +518,7 @@ gather_rows_kernel(const GatherArgs a, const int out_f32, const int normalize, c
       } else {
         base = a.base + (long long)img * a.image_stride; h = a.height; w = a.width;
       }
-      if (img >= a.n_images || y < 0 || x < 0 || (y + 1) * P > h || (x + 1) * P > w) {
+      if (img >= a.n_images || y < 0 || x < 0 || (y + 1) * P > grid_extent(a, h) || (x + 1) * P > grid_extent(a, w)) {
         if (a.status && lane == 0 && ch == 0 && r == 0) atomicOr(a.status, 1);
         continue;  // out-of-grid position: tile skipped
       }
@@ -582,7 +589,7 @@ __global__ void gather_ldg_kernel(const GatherArgs a, const int out_f32, const i
       } else {
         base = a.base + (long long)img * a.image_stride; h = a.height; w = a.width;
       }
-      if (img >= a.n_images || y < 0 || x < 0 || (y + 1) * P > h || (x + 1) * P > w) {
+      if (img >= a.n_images || y < 0 || x < 0 || (y + 1) * P > grid_extent(a, h) || (x + 1) * P > grid_extent(a, w)) {
         if (a.status && rem == 0 && ch == 0) atomicOr(a.status, 1);
         continue;
       }

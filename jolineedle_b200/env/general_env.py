@@ -19,6 +19,11 @@ Extensions (keyword-only, default = reference behaviour):
              shifted copy of the image made on the CPU.  The caller shifts the boxes (as the dataset does).
   device     upload CPU inputs to this CUDA device (the reference keeps everything on
              ``images.device``; there is no CPU path here)
+  zero_copy  pinned HOST images are not uploaded: every step reads the glimpsed tiles in place over PCIe,
+             and with ``history`` a patch an episode has already seen is served from the crop history in HBM
+  pad_to_patch  image sizes that are not multiples of the patch: the env behaves as if the images had been
+             zero-padded at the bottom / right (``padded_collate_fn``, dataset.py:307-347) without
+             materialising the padding (the TMA unit zero-fills what lies outside the image)
 """
 from typing import List, Optional, Tuple
 
@@ -47,6 +52,7 @@ class NeedleGeneralEnv:
         device=None,
         translate: Optional[Tensor] = None,
         zero_copy: bool = False,
+        pad_to_patch: bool = False,
     ):
         # same preconditions as general_env.py:37-39,50-51
         assert images.shape[0] == bboxes.shape[0]
@@ -71,10 +77,15 @@ class NeedleGeneralEnv:
         self.n_glimps_levels = n_glimps_levels
         self.stop_enabled = stop_enabled
         self.batch_size, self.n_channels, self.height, self.width = images.shape
-        assert self.height % self.patch_size == 0
-        assert self.width % self.patch_size == 0
-        self.n_vertical_patches = self.height // self.patch_size
-        self.n_horizontal_patches = self.width // self.patch_size
+        # pad_to_patch: sizes that are not multiples of the patch behave as if the images had been zero-padded at
+        # the bottom / right (padded_collate_fn, dataset.py:307-347) -- the gather zero-fills what lies outside
+        if not pad_to_patch:
+            assert self.height % self.patch_size == 0
+            assert self.width % self.patch_size == 0
+        elif n_glimps_levels != 1:
+            raise NotImplementedError("pad_to_patch serves one glimpse level")
+        self.n_vertical_patches = -(-self.height // self.patch_size)
+        self.n_horizontal_patches = -(-self.width // self.patch_size)
         self.device = torch.device(device) if self._zero_copy else images.device
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -89,7 +100,8 @@ class NeedleGeneralEnv:
             self._shifts = t.to(torch.int32).flip(1).contiguous().to(self.device)
 
         if n_glimps_levels == 1:
-            self._set = ImageSet(images, patch_size, device=self.device if self._zero_copy else None)
+            self._set = ImageSet(images, patch_size, device=self.device if self._zero_copy else None,
+                                 pad_to_patch=pad_to_patch)
             # [B, G=1, C, H, W] view of the caller's tensor (callers read env.images[0, 0]); the reflect-pad +
             # resize the reference computes and throws away at one level (general_env.py:95-111) is not done
             self.images = self._set._slabs[0].unsqueeze(1)

@@ -18,10 +18,15 @@ TIMING: Optional[list] = None
 
 
 class ImageSet:
-    def __init__(self, images: Union[torch.Tensor, Sequence[torch.Tensor]], patch_size: int, device=None):
+    def __init__(self, images: Union[torch.Tensor, Sequence[torch.Tensor]], patch_size: int, device=None,
+                 pad_to_patch: bool = False):
         """``device`` is only needed for *pinned host* images: those are not uploaded -- the
         gather kernels read the tiles they need straight out of the page-locked host memory
-        (same pointer under unified addressing), so only glimpsed pixels ever cross PCIe."""
+        (same pointer under unified addressing), so only glimpsed pixels ever cross PCIe.
+
+        ``pad_to_patch``: image sizes need not be multiples of ``patch_size``; the set behaves as if
+        every image had been zero-padded at the bottom / right (``complete_to_patch_size`` /
+        ``padded_collate_fn``, dataset.py:307-347,379-406) without materialising the padding."""
         slabs: List[torch.Tensor] = [images] if isinstance(images, torch.Tensor) else list(images)
         if not slabs:
             raise ValueError("empty image set")
@@ -56,6 +61,7 @@ class ImageSet:
             raise ValueError(f"images live on {cuda_device} but the set was asked for {self.device}")
         self.dtype, self.channels = dtype, channels
         self.patch_size = int(patch_size)
+        self.pad_to_patch = bool(pad_to_patch)
         self._slabs = norm  # keeps the memory alive
         self.counts, self.heights, self.widths = counts, heights, widths
         self.n_images = sum(counts)
@@ -71,7 +77,8 @@ class ImageSet:
         a_ptrs = np.array(ptrs, dtype=np.uint64)
         a_dims = np.array([counts, heights, widths], dtype=np.int32)  # rows are contiguous int32 arrays
         with _cabi.on_device(self.device):
-            rc = _cabi.lib().jn_images_create(
+            create = _cabi.lib().jn_images_create_padded if pad_to_patch else _cabi.lib().jn_images_create
+            rc = create(
                 ctypes.byref(handle), n, a_ptrs.ctypes.data, a_dims[0].ctypes.data, a_dims[1].ctypes.data,
                 a_dims[2].ctypes.data, channels,
                 _cabi.dtype_code(dtype), self.patch_size, _cabi.ptr(self._table_host), _cabi.ptr(self._table),
