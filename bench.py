@@ -401,7 +401,7 @@ def main():
     wl = cls(args.batch or default_batch, rank, device, src)
     # nvidia-smi is started here, seconds before the timed region: its NVML start-up stalls CUDA calls
     clocks = ClockSampler(local_rank)
-    if not args.no_clocks:
+    if not args.no_clocks and rank == 0:  # rank 0's GPU stands for the box: one poller, not one per rank
         clocks.__enter__()
     wl.to_device()
     peaks = {}

@@ -22,6 +22,11 @@ __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(kFullM
 // rule 1 (area 5%): simple_env.py:270-321 -- patch set iff it lies in the box's patch range
 //   and 20 * overlap_area > P^2 (the float test `area / P**2 > 0.05` in exact integers), or
 //   it holds the box centre; always restricted to the grid.
+//
+// One warp per episode.  Boxes are taken one at a time (their patch ranges are warp-uniform scalars); for the
+// few bitmap words a box can touch, lane = bit evaluates its patch and a ballot assembles the word, which
+// lane (word % 32) ORs into its accumulator -- so a 5x6 grid keeps 30 lanes busy instead of one, and a
+// 32x32 grid only visits the one or two words under each box.
 __global__ void patch_bitmaps_kernel(const int64_t* __restrict__ bboxes, const int32_t* __restrict__ n_boxes, int n,
                                      int max_boxes, int P, int grid_rows, int grid_cols,
                                      const int32_t* __restrict__ rows_arr, const int32_t* __restrict__ cols_arr,
@@ -34,8 +39,8 @@ __global__ void patch_bitmaps_kernel(const int64_t* __restrict__ bboxes, const i
     const int nb = n_boxes ? n_boxes[e] : max_boxes;
     const long long H = (long long)rows * P, W = (long long)cols * P;
     const int n_bits = rows * cols;
-    for (int w = lane; w < words_per_item; w += 32) {
-      uint32_t word = 0;
+    for (int wb = 0; wb < words_per_item; wb += 32) {  // blocks of 32 words: lane l accumulates word wb + l
+      uint32_t acc = 0;
       for (int k = 0; k < nb; ++k) {
         const int64_t* b = bboxes + ((long long)e * max_boxes + k) * 4;
         const long long x1 = b[0], y1 = b[1], x2 = b[2], y2 = b[3];
@@ -50,25 +55,37 @@ __global__ void patch_bitmaps_kernel(const int64_t* __restrict__ bboxes, const i
           px_lo = floordiv(x1, P); px_hi = floordiv(x2, P); py_lo = floordiv(y1, P); py_hi = floordiv(y2, P);
           cpx = floordiv(floordiv(x1 + x2, 2), P); cpy = floordiv(floordiv(y1 + y2, 2), P);
         }
-        for (int bit = 0; bit < 32; ++bit) {
-          const int idx = w * 32 + bit;
-          if (idx >= n_bits) break;
-          const int y = idx / cols, x = idx - y * cols;
-          bool hit;
-          if (rule == 0) {
-            hit = (x >= px_lo && x <= px_hi && y >= py_lo && y <= py_hi);
-          } else {
-            hit = (x == cpx && y == cpy);
-            if (!hit && x >= px_lo && x <= px_hi && y >= py_lo && y <= py_hi) {
-              const long long oh = lmin((long long)(y + 1) * P, y2) - lmax((long long)y * P, y1);
-              const long long ow = lmin((long long)(x + 1) * P, x2) - lmax((long long)x * P, x1);
-              hit = 20 * (oh * ow) > (long long)P * P;
+        // bits the box can set: its patch range clipped to the grid, plus the centre patch when that is in the grid
+        const long long cx_lo = lmax(px_lo, 0), cx_hi = lmin(px_hi, cols - 1);
+        const long long cy_lo = lmax(py_lo, 0), cy_hi = lmin(py_hi, rows - 1);
+        long long idx_lo = n_bits, idx_hi = -1;
+        if (cx_lo <= cx_hi && cy_lo <= cy_hi) { idx_lo = cy_lo * cols + cx_lo; idx_hi = cy_hi * cols + cx_hi; }
+        if (rule != 0 && cpx >= 0 && cpx < cols && cpy >= 0 && cpy < rows) {
+          idx_lo = lmin(idx_lo, cpy * cols + cpx); idx_hi = lmax(idx_hi, cpy * cols + cpx);
+        }
+        if (idx_hi < idx_lo) continue;
+        const int w_lo = imax((int)(idx_lo >> 5), wb), w_hi = imin((int)(idx_hi >> 5), imin(wb + 31, words_per_item - 1));
+        for (int w = w_lo; w <= w_hi; ++w) {
+          const int idx = w * 32 + lane;
+          bool hit = false;
+          if (idx < n_bits) {
+            const int y = idx / cols, x = idx - y * cols;
+            if (rule == 0) {
+              hit = (x >= px_lo && x <= px_hi && y >= py_lo && y <= py_hi);
+            } else {
+              hit = (x == cpx && y == cpy);
+              if (!hit && x >= px_lo && x <= px_hi && y >= py_lo && y <= py_hi) {
+                const long long oh = lmin((long long)(y + 1) * P, y2) - lmax((long long)y * P, y1);
+                const long long ow = lmin((long long)(x + 1) * P, x2) - lmax((long long)x * P, x1);
+                hit = 20 * (oh * ow) > (long long)P * P;
+              }
             }
           }
-          if (hit) word |= 1u << bit;
+          const uint32_t word = __ballot_sync(kFullMask, hit);
+          if (lane == w - wb) acc |= word;
         }
       }
-      out[(long long)e * words_per_item + w] = word;
+      if (wb + lane < words_per_item) out[(long long)e * words_per_item + wb + lane] = acc;
     }
   }
 }
