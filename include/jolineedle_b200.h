@@ -295,6 +295,15 @@ int jn_plan_run(jn_plan* plan, int n, const int64_t* boxes, const int32_t* n_box
                 const int32_t* rows, const int32_t* cols, int patch_size, const uint64_t* seeds,
                 const uint8_t* has_seed, int min_keypoints, int max_keypoints, int binomial,
                 const int32_t* start_yx, uint32_t* mt_state);
+/* The same on a thread of the library's own: jn_plan_start returns at once, jn_plan_wait joins and returns
+ * jn_plan_run's status.  The caller keeps every input array alive and untouched in between and calls nothing
+ * else on the plan; a host language with a global interpreter lock can so overlap the planning of a batch with
+ * its own work on the same batch (building the image set). */
+int jn_plan_start(jn_plan* plan, int n, const int64_t* boxes, const int32_t* n_boxes, int max_boxes,
+                  const int32_t* rows, const int32_t* cols, int patch_size, const uint64_t* seeds,
+                  const uint8_t* has_seed, int min_keypoints, int max_keypoints, int binomial,
+                  const int32_t* start_yx, uint32_t* mt_state);
+int jn_plan_wait(jn_plan* plan);
 int jn_plan_sizes(const jn_plan* plan, int* n_segments, int* n_draws, int* n_det);
 /* start [n,2], seg_begin [n+1], seg_to [S,2], seg_tgt [S,2], draw_begin [n+1], det_begin [n+1],
  * det_yx [D,2] (int32); seg_flags [S], draws [Q] (uint8).  NULL pointers are skipped. */

@@ -61,6 +61,8 @@ SIGNATURES = {
     "jn_plan_destroy": (None, [_P]),
     "jn_plan_error": (c_char_p, [_P]),
     "jn_plan_run": (c_int, [_P, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P]),
+    "jn_plan_start": (c_int, [_P, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P]),
+    "jn_plan_wait": (c_int, [_P]),
     "jn_plan_sizes": (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "jn_plan_export": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }

@@ -24,6 +24,7 @@
 #include <cstring>
 #include <memory>
 #include <random>
+#include <thread>
 #include <vector>
 
 #include "../../include/jolineedle_b200.h"
@@ -403,6 +404,9 @@ struct jn_plan {
   std::vector<Cell> visited, empties, keypoints, ties;
   std::vector<int64_t> slots;
   std::vector<PySet> cells;
+  // jn_plan_start / jn_plan_wait
+  std::thread worker;
+  int worker_status = JN_OK;
 };
 
 namespace {
@@ -446,7 +450,10 @@ int jn_plan_create(jn_plan** out) {
   *out = new jn_plan();
   return JN_OK;
 }
-void jn_plan_destroy(jn_plan* p) { delete p; }
+void jn_plan_destroy(jn_plan* p) {
+  if (p && p->worker.joinable()) p->worker.join();
+  delete p;
+}
 const char* jn_plan_error(const jn_plan* p) { return p ? p->error : "null plan"; }
 
 int jn_plan_run(jn_plan* plan, int n, const int64_t* boxes, const int32_t* n_boxes, int max_boxes,
@@ -568,6 +575,30 @@ int jn_plan_run(jn_plan* plan, int n, const int64_t* boxes, const int32_t* n_box
     o.final_pos.push_back(ep.pos.y); o.final_pos.push_back(ep.pos.x);
   }
   return JN_OK;
+}
+
+int jn_plan_start(jn_plan* plan, int n, const int64_t* boxes, const int32_t* n_boxes, int max_boxes,
+                  const int32_t* rows, const int32_t* cols, int patch_size, const uint64_t* seeds,
+                  const uint8_t* has_seed, int min_keypoints, int max_keypoints, int binomial,
+                  const int32_t* start_yx, uint32_t* mt_state) {
+  if (!plan || plan->worker.joinable()) return JN_ERR_INVALID;  // one run at a time
+  plan->worker_status = JN_OK;
+  try {
+    plan->worker = std::thread([=] {
+      plan->worker_status = jn_plan_run(plan, n, boxes, n_boxes, max_boxes, rows, cols, patch_size, seeds, has_seed,
+                                        min_keypoints, max_keypoints, binomial, start_yx, mt_state);
+    });
+  } catch (...) {  // no thread to be had: plan on the caller's
+    plan->worker_status = jn_plan_run(plan, n, boxes, n_boxes, max_boxes, rows, cols, patch_size, seeds, has_seed,
+                                      min_keypoints, max_keypoints, binomial, start_yx, mt_state);
+  }
+  return JN_OK;
+}
+
+int jn_plan_wait(jn_plan* plan) {
+  if (!plan) return JN_ERR_INVALID;
+  if (plan->worker.joinable()) plan->worker.join();
+  return plan->worker_status;
 }
 
 int jn_plan_sizes(const jn_plan* p, int* n_segments, int* n_draws, int* n_det) {

@@ -113,12 +113,19 @@ def native_supported(rows: np.ndarray, cols: np.ndarray, exact_boxes: bool, seed
     return True
 
 
-def plan_native(boxes: np.ndarray, n_boxes: np.ndarray, n_max: int, rows: np.ndarray, cols: np.ndarray,
-                patch_size: int, seeds: Optional[Sequence[Optional[int]]], min_keypoints: int, max_keypoints: int,
-                binomial_keypoints: bool, position: Optional[Position]) -> PackedPlans:
-    """Run ``jn_plan_run`` on the host.  Python's global ``random`` state is handed to the C++
-    side and written back, so interleaving with other users of ``random`` behaves as if
-    ``random.choice`` had been called from python."""
+class _PlanTicket:
+    """A native plan in flight (``jn_plan_start``): the input arrays it reads, kept alive until ``finish``."""
+
+    __slots__ = ("arrays", "mt", "version", "gauss", "n", "n_max")
+
+
+def plan_native_start(boxes: np.ndarray, n_boxes: np.ndarray, n_max: int, rows: np.ndarray, cols: np.ndarray,
+                      patch_size: int, seeds: Optional[Sequence[Optional[int]]], min_keypoints: int,
+                      max_keypoints: int, binomial_keypoints: bool, position: Optional[Position]) -> _PlanTicket:
+    """Start ``jn_plan_run`` on a thread of the library (no GIL involved); :func:`plan_native_finish` joins it.
+    Python's global ``random`` state is handed to the C++ side and written back at the end, so
+    interleaving with other users of ``random`` behaves as if ``random.choice`` had been called from
+    python -- provided nobody touches ``random`` between start and finish."""
     global _native_plan
     if _native_plan is None:
         _native_plan = _NativePlan()
@@ -138,16 +145,29 @@ def plan_native(boxes: np.ndarray, n_boxes: np.ndarray, n_max: int, rows: np.nda
         start = np.tile(np.array([int(position[0]), int(position[1])], dtype=np.int32), (n, 1))
     version, mt_words, gauss = random.getstate()
     mt = np.array(mt_words, dtype=np.uint32)
-    rc = lib.jn_plan_run(h, n, boxes.ctypes.data, n_boxes.ctypes.data, boxes.shape[1] if n_max > 0 else 0,
-                         rows.ctypes.data, cols.ctypes.data, patch_size, seed_arr.ctypes.data, has_seed.ctypes.data,
-                         min_keypoints, max_keypoints, 1 if binomial_keypoints else 0,
-                         None if start is None else start.ctypes.data, mt.ctypes.data)
+    rc = lib.jn_plan_start(h, n, boxes.ctypes.data, n_boxes.ctypes.data, boxes.shape[1] if n_max > 0 else 0,
+                           rows.ctypes.data, cols.ctypes.data, patch_size, seed_arr.ctypes.data, has_seed.ctypes.data,
+                           min_keypoints, max_keypoints, 1 if binomial_keypoints else 0,
+                           None if start is None else start.ctypes.data, mt.ctypes.data)
+    if rc != _cabi.JN_OK:
+        raise _cabi.NativeLibraryError(f"native planner could not start (status {rc}): a plan is already running")
+    t = _PlanTicket()
+    t.arrays = (boxes, n_boxes, rows, cols, seed_arr, has_seed, start)
+    t.mt, t.version, t.gauss, t.n, t.n_max = mt, version, gauss, n, n_max
+    return t
+
+
+def plan_native_finish(t: _PlanTicket) -> PackedPlans:
+    lib, h = _cabi.lib(), _native_plan.handle
+    rc = lib.jn_plan_wait(h)
     if rc != _cabi.JN_OK:
         msg = lib.jn_plan_error(h).decode("utf-8", "replace")
         if rc == _cabi.JN_ERR_INVALID:
             raise AssertionError(msg)  # e.g. start position outside the grid (simple_env.py:73-74)
         raise _cabi.NativeLibraryError(f"native planner failed (status {rc}): {msg}")
-    random.setstate((version, tuple(mt.tolist()), gauss))
+    random.setstate((t.version, tuple(t.mt.tolist()), t.gauss))
+    n = t.n
+    boxes, n_boxes, rows, cols = t.arrays[:4]
     n_seg, n_draw, n_det = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     lib.jn_plan_sizes(h, ctypes.byref(n_seg), ctypes.byref(n_draw), ctypes.byref(n_det))
     p = PackedPlans()
@@ -164,8 +184,16 @@ def plan_native(boxes: np.ndarray, n_boxes: np.ndarray, n_max: int, rows: np.nda
     lib.jn_plan_export(h, p.start.ctypes.data, p.seg_begin.ctypes.data, p.seg_to.ctypes.data, p.seg_tgt.ctypes.data,
                        p.draw_begin.ctypes.data, p.det_begin.ctypes.data, p.det_yx.ctypes.data,
                        p.seg_flags.ctypes.data, p.draws.ctypes.data)
-    p.rows, p.cols, p.n_boxes, p.boxes, p.n_max = rows, cols, n_boxes, boxes, n_max
+    p.rows, p.cols, p.n_boxes, p.boxes, p.n_max = rows, cols, n_boxes, boxes, t.n_max
     return p
+
+
+def plan_native(boxes: np.ndarray, n_boxes: np.ndarray, n_max: int, rows: np.ndarray, cols: np.ndarray,
+                patch_size: int, seeds: Optional[Sequence[Optional[int]]], min_keypoints: int, max_keypoints: int,
+                binomial_keypoints: bool, position: Optional[Position]) -> PackedPlans:
+    """Run ``jn_plan_run`` on the host and wait for it."""
+    return plan_native_finish(plan_native_start(boxes, n_boxes, n_max, rows, cols, patch_size, seeds, min_keypoints,
+                                                max_keypoints, binomial_keypoints, position))
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -317,8 +345,11 @@ def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normaliz
 def plan_batch(bboxes: Sequence[Sequence], heights: Sequence[int], widths: Sequence[int], patch_size: int,
                min_keypoints: int, max_keypoints: int, binomial_keypoints: bool = False,
                position: Optional[Position] = None, seeds: Optional[Sequence[Optional[int]]] = None,
-               planner: str = "auto") -> PackedPlans:
-    """Host half for a batch of images given only their sizes and boxes (no pixel is touched)."""
+               planner: str = "auto", deferred: bool = False):
+    """Host half for a batch of images given only their sizes and boxes (no pixel is touched).
+    ``deferred``: return a zero-argument callable that yields the plans -- with the native planner the work
+    then runs on a library thread while the caller goes on (``generate_trajectories`` builds the image set
+    meanwhile)."""
     for h, w in zip(heights, widths):
         # same precondition as get_patch (simple_env.py:68-69)
         assert h % patch_size == 0 and w % patch_size == 0, f"image {h}x{w} is not a multiple of {patch_size}"
@@ -331,8 +362,9 @@ def plan_batch(bboxes: Sequence[Sequence], heights: Sequence[int], widths: Seque
     if planner == "native" and not use_native:
         raise ValueError("the native planner needs integer boxes, grids up to 60x60 and seeds below 2**64")
     if use_native:
-        return plan_native(boxes, n_boxes, n_max, rows, cols, patch_size, seeds, min_keypoints, max_keypoints,
-                           binomial_keypoints, position)
+        ticket = plan_native_start(boxes, n_boxes, n_max, rows, cols, patch_size, seeds, min_keypoints, max_keypoints,
+                                   binomial_keypoints, position)
+        return (lambda: plan_native_finish(ticket)) if deferred else plan_native_finish(ticket)
     from .simple_env import NeedleSimpleEnv
 
     class _Shape:  # plan_sample only needs the image's shape
@@ -343,7 +375,8 @@ def plan_batch(bboxes: Sequence[Sequence], heights: Sequence[int], widths: Seque
     envs = [NeedleSimpleEnv(_Shape(heights[i], widths[i]), patch_size, bboxes[i], None if seeds is None else seeds[i])
             for i in range(len(bboxes))]
     plans = [e.plan_sample(min_keypoints, max_keypoints, binomial_keypoints, position) for e in envs]
-    return pack_python_plans(envs, plans)
+    packed = pack_python_plans(envs, plans)
+    return (lambda: packed) if deferred else packed
 
 
 def generate_trajectories(
@@ -374,9 +407,12 @@ def generate_trajectories(
         # images have to be staged through a full upload.
         images = [im if (im.is_cuda or (zero_copy and im.is_pinned())) else im.to(device, non_blocking=True)
                   for im in images]
-    packed = plan_batch(batch["bboxes"], [im.shape[1] for im in images], [im.shape[2] for im in images], patch_size,
-                        min_keypoints, max_keypoints, binomial_keypoints, position, seeds, planner)
-    image_set = ImageSet(images, patch_size, device=device)
+    plans = plan_batch(batch["bboxes"], [im.shape[1] for im in images], [im.shape[2] for im in images], patch_size,
+                       min_keypoints, max_keypoints, binomial_keypoints, position, seeds, planner, deferred=True)
+    try:
+        image_set = ImageSet(images, patch_size, device=device)  # while the native planner runs on its own thread
+    finally:
+        packed = plans()  # always joined: the planner reads arrays that die with this frame
     out = expand_packed(image_set, packed, max_seq_len, normalize, engine)
     class_id = np.array([int(c) for c in batch["class_id"]], dtype=np.int64)
     out["class_id"] = _upload(class_id, image_set.device)
