@@ -215,3 +215,38 @@ def test_best_next_action_equals_reference_eval_oracle():
             assert env.rng.bit_generator.state == np_ref
             checked += 1
     assert checked >= 100
+
+
+def test_native_planner_on_its_own_thread_matches_the_blocking_call():
+    """jn_plan_start / jn_plan_wait: same plans, same advanced `random` state; one run at a time; errors surface
+    at the join."""
+    import random
+
+    import pytest
+
+    from jolineedle_b200 import _cabi
+    from jolineedle_b200.env import trajectories as tj
+
+    P, heights, widths, bboxes = _random_case(np.random.default_rng(31), 40)
+    seeds = list(range(500, 540))
+    random.seed(9)
+    want = tj.plan_batch(bboxes, heights, widths, P, 0, 3, True, None, seeds, planner="native")
+    state_after = random.getstate()
+    random.seed(9)
+    finish = tj.plan_batch(bboxes, heights, widths, P, 0, 3, True, None, seeds, planner="native", deferred=True)
+    # a second start while the first is in flight is refused, not queued
+    rows = np.array([h // P for h in heights], dtype=np.int32)
+    lib, handle = _cabi.lib(), tj._native_plan.handle
+    mt = np.zeros(625, dtype=np.uint32)
+    rc = lib.jn_plan_start(handle, 0, None, None, 0, rows.ctypes.data, rows.ctypes.data, P, None, None, 0, 0, 0, None,
+                           mt.ctypes.data)
+    assert rc == _cabi.JN_ERR_INVALID
+    got = finish()
+    assert random.getstate() == state_after
+    _assert_same_plans(want, got)
+    # a start position outside the grid is reported by the join, as the reference's assert (simple_env.py:73-74)
+    finish = tj.plan_batch(bboxes, heights, widths, P, 0, 3, True, Position(99, 0), seeds, planner="native", deferred=True)
+    with pytest.raises(AssertionError):
+        finish()
+    again = tj.plan_batch(bboxes, heights, widths, P, 0, 3, True, None, seeds, planner="native")  # usable again
+    assert again.n == want.n
