@@ -103,7 +103,9 @@ static inline int64_t jn_images_table_bytes(int64_t n_images) { return n_images 
  * image had been zero-padded at the bottom / right up to the next multiple (complete_to_patch_size and
  * padded_collate_fn, dataset.py:307-347,379-406) -- the patch grid is ceil(H/P) x ceil(W/P) and the pixels
  * of the edge tiles that lie outside the image are zeros -- without materialising the padding (the TMA unit
- * zero-fills out-of-bounds bytes; sets the tensor engine cannot address fall back to plain loads). */
+ * zero-fills out-of-bounds bytes; sets the tensor engine cannot address fall back to plain loads).  With
+ * `shifts`, the image is translated inside its own H x W frame first and padded afterwards (the dataset's order:
+ * transform, then collate), i.e. tile pixels whose frame coordinate lies in the padding are zeros. */
 int jn_images_create_padded(jn_images** out, int n_slabs, const void* const* slab_ptrs /*HOST*/,
                             const int32_t* counts /*HOST*/, const int32_t* heights /*HOST*/,
                             const int32_t* widths /*HOST*/, int channels, int dtype /*jn_dtype*/,

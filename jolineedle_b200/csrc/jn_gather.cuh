@@ -199,9 +199,17 @@ enum XformMode { kNormPlain = 0, kF32Focus = 1, kNormFocus = 2, kF32Plain = 3 };
 struct __align__(16) StageDesc {
   unsigned long long dst;  // first byte of the chunk's output item
   int chrow;               // channel << 16 | first tile row
-  int flags;               // kDescSkip | kDescZero | residual byte offset << 8
+  int flags;               // kDescSkip | kDescZero | kDescStop | residual byte offset << 8 | frame limits (below)
 };
 constexpr int kDescSkip = 1, kDescZero = 2, kDescStop = 4;
+// Translated gathers out of padded sets: the translated image is clipped to its own H x W frame before the
+// padding (dataset order: transform, then padded_collate_fn), so tile pixels whose FRAME coordinate lies in the
+// padding are zeros even if the shifted source pixel exists.  Per chunk: rows / columns of the tile that are
+// inside the frame (rows <= 256 -> 9 bits at 12, columns <= 2047 -> 11 bits at 21).
+__device__ __forceinline__ int desc_pack_limits(int row_lim, int col_lim) { return (row_lim << 12) | (col_lim << 21); }
+__device__ __forceinline__ int desc_offset(int flags) { return ((unsigned)flags >> 8) & 15; }
+__device__ __forceinline__ int desc_row_limit(int flags) { return ((unsigned)flags >> 12) & 511; }
+__device__ __forceinline__ int desc_col_limit(int flags) { return (unsigned)flags >> 21; }
 
 // 4 staged source pixels of group g of a staged row (uint8: one word; float32: one float4)
 template <bool kShift>
@@ -225,6 +233,23 @@ __device__ __forceinline__ float4 staged_f32x4(const uint8_t* row, int g, int of
   }
 }
 
+// Zero the pixels of group (row i / wpr, columns 4g .. 4g+3) that lie outside the frame limits.
+__device__ __forceinline__ uint32_t clip_u8x4(uint32_t u, int i, int g, int rows, int wpr, uint32_t magic, int row_lim,
+                                             int col_lim) {
+  const int r = (int)__umulhi((uint32_t)i, magic), gg = i - r * wpr;
+  (void)g; (void)rows;
+  const int valid = col_lim - 4 * gg;  // pixels of this group inside the frame
+  if (r >= row_lim || valid <= 0) return 0u;
+  return valid >= 4 ? u : (u & (0xFFFFFFFFu >> (8 * (4 - valid))));
+}
+__device__ __forceinline__ float4 clip_f32x4(float4 v, int i, int g, int rows, int wpr, uint32_t magic, int row_lim,
+                                             int col_lim) {
+  const int r = (int)__umulhi((uint32_t)i, magic), gg = i - r * wpr;
+  (void)g; (void)rows;
+  const int valid = (r >= row_lim) ? 0 : col_lim - 4 * gg;
+  return make_float4(valid > 0 ? v.x : 0.f, valid > 1 ? v.y : 0.f, valid > 2 ? v.z : 0.f, valid > 3 ? v.w : 0.f);
+}
+
 template <int kMode, bool kShift>
 __device__ __forceinline__ void xform_chunk(const GatherArgs& a, const StageDesc& d, const uint8_t* stage, int tid,
                                             int nthreads) {
@@ -233,8 +258,11 @@ __device__ __forceinline__ void xform_chunk(const GatherArgs& a, const StageDesc
   const int P = a.patch, wpr = P >> 2;  // wpr = 4-pixel groups per row
   const int n = a.rows * wpr, pitch = a.pitch;
   const uint32_t magic = a.wpr_magic;  // ceil(2^32 / wpr): i / wpr == umulhi(i, magic) for every i < n
-  const int ch = d.chrow >> 16, row0 = d.chrow & 0xFFFF, off = d.flags >> 8;
+  const int ch = d.chrow >> 16, row0 = d.chrow & 0xFFFF, off = desc_offset(d.flags);
   const bool zero = (d.flags & kDescZero) != 0;
+  // frame clipping (translated + padded sets only): uniform over the chunk
+  const int row_lim = kShift ? desc_row_limit(d.flags) : a.rows, col_lim = kShift ? desc_col_limit(d.flags) : P;
+  const bool clip = kShift && (row_lim < a.rows || col_lim < P);
   float* out_item = reinterpret_cast<float*>(d.dst);
   if (kMode == kNormPlain || kMode == kF32Plain) {
     // rows * P source pixels in, rows * P floats out, contiguous in the output
@@ -253,10 +281,12 @@ __device__ __forceinline__ void xform_chunk(const GatherArgs& a, const StageDesc
         row = stage + r * pitch;
       }
       if (kMode == kNormPlain) {
-        const uint32_t u = staged_u8x4<kShift>(row, g, off);
+        uint32_t u = staged_u8x4<kShift>(row, g, off);
+        if (clip) u = clip_u8x4(u, i, g, a.rows, wpr, magic, row_lim, col_lim);
         st_f4(dst + 4 * i, byte_to_unit<0>(u), byte_to_unit<1>(u), byte_to_unit<2>(u), byte_to_unit<3>(u));
       } else {
-        const float4 v = staged_f32x4<kShift>(row, g, off);
+        float4 v = staged_f32x4<kShift>(row, g, off);
+        if (clip) v = clip_f32x4(v, i, g, a.rows, wpr, magic, row_lim, col_lim);
         st_f4(dst + 4 * i, v.x, v.y, v.z, v.w);
       }
     }
@@ -281,10 +311,12 @@ __device__ __forceinline__ void xform_chunk(const GatherArgs& a, const StageDesc
       const int gi = kShift ? g : i;
       float e0, o0, e1, o1;
       if (kMode == kF32Focus) {
-        const float4 v = staged_f32x4<kShift>(row, gi, off);
+        float4 v = staged_f32x4<kShift>(row, gi, off);
+        if (clip) v = clip_f32x4(v, i, g, a.rows, wpr, magic, row_lim, col_lim);
         e0 = v.x; o0 = v.y; e1 = v.z; o1 = v.w;
       } else {
-        const uint32_t u = staged_u8x4<kShift>(row, gi, off);
+        uint32_t u = staged_u8x4<kShift>(row, gi, off);
+        if (clip) u = clip_u8x4(u, i, g, a.rows, wpr, magic, row_lim, col_lim);
         e0 = byte_to_unit<0>(u); o0 = byte_to_unit<1>(u); e1 = byte_to_unit<2>(u); o1 = byte_to_unit<3>(u);
       }
       float* even = base + ((r & 1) * dy_planes + (r >> 1) * half + 2 * g);
@@ -359,6 +391,10 @@ __device__ __forceinline__ ChunkPlan plan_chunk(const GatherArgs& a, int q, bool
     p.flags |= (xb - xa) << 8;
     p.cx = xa >> 3;                                // in 8-byte map elements
     p.cy = py * a.patch + row0 - sy;
+    // rows / columns of this chunk inside the image's own frame (everything, unless the set is padded)
+    const int row_lim = a.padded ? imax(0, imin(a.rows, h - (py * a.patch + row0))) : a.rows;
+    const int col_lim = a.padded ? imax(0, imin(a.patch, w - px * a.patch)) : a.patch;
+    p.flags |= desc_pack_limits(row_lim, col_lim);
   } else {
     p.cx = px * a.kbox;
     p.cy = py * a.patch + row0;
@@ -525,7 +561,8 @@ gather_rows_kernel(const GatherArgs a, const int out_f32, const int normalize, c
     }
     const long long sy = zero_row ? -1 : y * P + r - (a.shifts ? a.shifts[2 * img] : 0);
     const long long sx0 = zero_row ? 0 : x * P - (a.shifts ? a.shifts[2 * img + 1] : 0);
-    const bool row_ok = !zero_row && sy >= 0 && sy < h;
+    // (padded sets: the translated image is clipped to its own frame before the padding)
+    const bool row_ok = !zero_row && sy >= 0 && sy < h && y * P + r < h;
     const uint8_t* row = row_ok ? base + (((long long)ch * h + sy) * w) * a.elem : nullptr;
     uint8_t* dst_item = a.out + (long long)item * a.out_item_stride;
     for (int g = lane; g < P / 4; g += 32) {
@@ -534,7 +571,7 @@ gather_rows_kernel(const GatherArgs a, const int out_f32, const int normalize, c
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const long long sx = sx0 + 4 * g + k;
-        if (row_ok && sx >= 0 && sx < w) {
+        if (row_ok && sx >= 0 && sx < w && x * P + 4 * g + k < w) {
           if (a.elem == 4) {
             f[k] = reinterpret_cast<const float*>(row)[sx];
           } else {
@@ -595,7 +632,7 @@ __global__ void gather_ldg_kernel(const GatherArgs a, const int out_f32, const i
       }
       const long long sy = y * P + r - (a.shifts ? a.shifts[2 * img] : 0);
       const long long sx = x * P + col - (a.shifts ? a.shifts[2 * img + 1] : 0);
-      if (sy >= 0 && sy < h && sx >= 0 && sx < w) {  // outside the (translated) image: zero fill
+      if (sy >= 0 && sy < h && sx >= 0 && sx < w && y * P + r < h && x * P + col < w) {  // outside the (translated) image or its frame: zero fill
         const long long e = ((long long)ch * h + sy) * w + sx;
         if (a.elem == 4) {
           fv = reinterpret_cast<const float*>(base)[e];

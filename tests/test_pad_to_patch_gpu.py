@@ -78,3 +78,28 @@ def test_env_on_unpadded_images_equals_env_on_padded_copies():
     env.check_status()
     with pytest.raises(AssertionError):
         NeedleGeneralEnv(u8.cuda(), boxes, P, T, 1, True)
+
+
+@pytest.mark.parametrize("engine", ["auto", "ldg"])
+def test_padded_and_translated(engine):
+    """Both zero fills at once: the image is translated (F.affine semantics) inside its own frame first, then
+    padded to the patch grid -- what the reference's dataset does (transform, then padded_collate_fn)."""
+    from jolineedle_b200.gather import ImageSet
+    from oracle.gaze_oracle import translate_oracle
+
+    P, h, w, b = 64, 150, 208, 4
+    g = torch.Generator().manual_seed(8)
+    u8 = torch.randint(0, 256, (b, 3, h, w), dtype=torch.uint8, generator=g)
+    shifts_xy = np.array([(0, 0), (13, -7), (-40, 21), (70, 90)])
+    want_images = padded(translate_oracle(u8, shifts_xy), P)
+    gh, gw = want_images.shape[-2] // P, want_images.shape[-1] // P
+    pos = torch.tensor([[y, x] for y in range(gh) for x in range(gw)] * b, dtype=torch.int64)
+    src = torch.arange(b, dtype=torch.int32).repeat_interleave(gh * gw)
+    s = ImageSet(u8.cuda(), P, pad_to_patch=True)
+    d_shifts = torch.from_numpy(shifts_xy[:, ::-1].copy().astype(np.int32)).cuda()  # (ty, tx)
+    table = torch.from_numpy(load_golden("norm.npz")["u8_over_255"])
+    want = torch.stack([want_images[int(k)][:, y * P:(y + 1) * P, x * P:(x + 1) * P] for (y, x), k in zip(pos.tolist(), src.tolist())])
+    got = s.gather(pos.cuda(), src_index=src.cuda(), shifts=d_shifts, normalize=True, engine=engine)
+    assert torch.equal(got.cpu(), table[want.long()])
+    got = s.gather(pos.cuda(), src_index=src.cuda(), shifts=d_shifts, normalize=True, focus=True, engine=engine)
+    assert torch.equal(got.cpu(), focus_restatement(table[want.long()]))
