@@ -287,7 +287,8 @@ int jn_tile_dedupe(const int64_t* traj_positions, const int32_t* traj_src, int n
  *   mt_state uint32 [625]: the MT19937 words + index of python's global `random`
  *   (random.getstate()[1]); updated in place so the caller can random.setstate() afterwards.
  *
- * JN_ERR_UNSUPPORTED for grids wider than 60 patches (numpy switches binomial algorithms there).
+ * Binomial key points follow numpy (inversion up to n*p = 30, BTPE above).  JN_ERR_UNSUPPORTED for grids wider than
+ * 4096 patches.
  * ------------------------------------------------------------------------------------------ */
 typedef struct jn_plan jn_plan;
 int jn_plan_create(jn_plan** out);

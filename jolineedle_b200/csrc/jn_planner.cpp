@@ -9,7 +9,7 @@
 //
 //   * numpy.random.SeedSequence -> PCG64 (XSL-RR 128/64) -> next_uint32 buffering ->
 //     Generator.integers (Lemire, 32-bit path), Generator.choice(int) (== integers(0, n)),
-//     Generator.binomial (inversion, n*p <= 30)                      [numpy >= 1.17 stream]
+//     Generator.binomial (inversion for n*p <= 30, BTPE above)        [numpy >= 1.17 stream]
 //   * random.choice -> _randbelow_with_getrandbits -> MT19937 genrand_uint32  [CPython 3.x]
 //   * set: open addressing, LINEAR_PROBES = 9, perturb shift 5, growth at fill*5 >= mask*3,
 //     dummy entries on removal, set_merge fast paths; tuple hash = the xxHash-style combiner of
@@ -17,7 +17,7 @@
 //
 // tests/test_planner_cpu.py checks the result against the pure-python planner (which calls the
 // real numpy / random / set) on thousands of random episodes; the python planner stays the
-// fallback for inputs this file does not cover (float boxes, grids wider than 60 patches).
+// fallback for inputs this file does not cover (float boxes, seeds above 2^64).
 #include <cmath>
 #include <cstdint>
 #include <algorithm>
@@ -124,8 +124,10 @@ struct NumpyRng {
     }
     return low + (int64_t)(m >> 32);
   }
-  // Generator.binomial(n, p) by inversion (p <= 0.5, n * p <= 30)
+  // Generator.binomial(n, p) for p <= 0.5 (numpy's random_binomial: inversion up to n * p = 30, BTPE above)
   int64_t binomial(int64_t n, double p) {
+    if (n == 0 || p == 0.0) return 0;
+    if (p * (double)n > 30.0) return binomial_btpe(n, p);
     const double q = 1.0 - p, qn = std::exp((double)n * std::log(q)), np = (double)n * p;
     const double bound = std::fmin((double)n, np + 10.0 * std::sqrt(np * q + 1));
     int64_t X = 0;
@@ -142,6 +144,74 @@ struct NumpyRng {
       }
     }
     return X;
+  }
+  // BTPE (Kachitvichyanukul & Schmeiser 1988) exactly as numpy's random_binomial_btpe draws it: two doubles
+  // per trial (u scaled by p4, then v), the same four regions, the same squeeze / final acceptance tests in
+  // the same floating-point order.  p <= 0.5.
+  int64_t binomial_btpe(int64_t n, double p) {
+    const double r = std::fmin(p, 1.0 - p), q = 1.0 - r;
+    const double fm = (double)n * r + r;
+    const int64_t m = (int64_t)std::floor(fm);
+    const double p1 = std::floor(2.195 * std::sqrt((double)n * r * q) - 4.6 * q) + 0.5;
+    const double xm = (double)m + 0.5, xl = xm - p1, xr = xm + p1;
+    const double c = 0.134 + 20.5 / (15.3 + (double)m);
+    double a = (fm - xl) / (fm - xl * r);
+    const double laml = a * (1.0 + a / 2.0);
+    a = (xr - fm) / (xr * q);
+    const double lamr = a * (1.0 + a / 2.0);
+    const double p2 = p1 * (1.0 + 2.0 * c), p3 = p2 + c / laml, p4 = p3 + c / lamr;
+    const double nrq = (double)n * r * q;
+    for (;;) {
+      double u = next_double() * p4, v = next_double();
+      int64_t y;
+      if (u <= p1) {  // triangular centre: accepted at once
+        y = (int64_t)std::floor(xm - p1 * v + u);
+        return y;
+      }
+      if (u <= p2) {  // parallelogram
+        const double x = xl + (u - p1) / c;
+        v = v * c + 1.0 - std::fabs((double)m - x + 0.5) / p1;
+        if (v > 1.0) continue;
+        y = (int64_t)std::floor(x);
+      } else if (u <= p3) {  // left exponential tail
+        y = (int64_t)std::floor(xl + std::log(v) / laml);
+        if (y < 0 || v == 0.0) continue;
+        v = v * (u - p2) * laml;
+      } else {  // right exponential tail
+        y = (int64_t)std::floor(xr - std::log(v) / lamr);
+        if (y > n || v == 0.0) continue;
+        v = v * (u - p3) * lamr;
+      }
+      const int64_t k = y > m ? y - m : m - y;
+      if (!(k > 20 && (double)k < nrq / 2.0 - 1)) {  // explicit evaluation of f(y) / f(m)
+        const double s = r / q, aa = s * (double)(n + 1);
+        double F = 1.0;
+        if (m < y) {
+          for (int64_t i = m + 1; i <= y; i++) F *= (aa / (double)i - s);
+        } else if (m > y) {
+          for (int64_t i = y + 1; i <= m; i++) F /= (aa / (double)i - s);
+        }
+        if (v > F) continue;
+        return y;
+      }
+      // squeezes on log(v), then the Stirling-corrected bound
+      const double kk = (double)k;
+      const double rho = (kk / nrq) * ((kk * (kk / 3.0 + 0.625) + 0.16666666666666666) / nrq + 0.5);
+      const double t = -kk * kk / (2 * nrq);
+      const double A = std::log(v);
+      if (A < t - rho) return y;
+      if (A > t + rho) continue;
+      const double x1 = (double)(y + 1), f1 = (double)(m + 1), z = (double)(n + 1 - m), w = (double)(n - y + 1);
+      const double x2 = x1 * x1, f2 = f1 * f1, z2 = z * z, w2 = w * w;
+      if (A > (xm * std::log(f1 / x1) + ((double)(n - m) + 0.5) * std::log(z / w) +
+               (double)(y - m) * std::log(w * r / (x1 * q)) +
+               (13680. - (462. - (132. - (99. - 140. / f2) / f2) / f2) / f2) / f1 / 166320. +
+               (13680. - (462. - (132. - (99. - 140. / z2) / z2) / z2) / z2) / z / 166320. +
+               (13680. - (462. - (132. - (99. - 140. / x2) / x2) / x2) / x2) / x1 / 166320. +
+               (13680. - (462. - (132. - (99. - 140. / w2) / w2) / w2) / w2) / w / 166320.))
+        continue;
+      return y;
+    }
   }
 };
 
@@ -470,8 +540,8 @@ int jn_plan_run(jn_plan* plan, int n, const int64_t* boxes, const int32_t* n_box
   std::unique_ptr<std::random_device> entropy;  // only opened for unseeded episodes
   for (int e = 0; e < n; ++e) {
     const int R = rows[e], C = cols[e], nb = max_boxes > 0 ? n_boxes[e] : 0;
-    if (R < 1 || C < 1 || R > 60 || C > 60) {
-      snprintf(o.error, sizeof(o.error), "episode %d: grid %dx%d outside the native planner's range (binomial inversion needs <= 60)", e, R, C);
+    if (R < 1 || C < 1 || R > 4096 || C > 4096) {
+      snprintf(o.error, sizeof(o.error), "episode %d: grid %dx%d outside the native planner's range (1..4096)", e, R, C);
       return JN_ERR_UNSUPPORTED;
     }
     o.arena.reset();

@@ -6,8 +6,8 @@ Two planners produce the same :class:`PackedPlans`:
   ``native``  ``jn_plan_run`` (csrc/jn_planner.cpp): the reference's random streams (numpy
               PCG64 / python MT19937 / CPython set order) restated in C++; ~1 us per episode.
   ``python``  ``NeedleSimpleEnv.plan_sample``: calls the real numpy / random / set objects;
-              used for inputs the native planner does not cover (float boxes, grids wider than
-              60 patches, seeds above 2^64) and as its cross-check in the tests.
+              used for inputs the native planner does not cover (float boxes, seeds above
+              2^64) and as its cross-check in the tests.
 
 The device half (:func:`expand_packed`) is shared: K0 5 %-area bitmaps, K3 ``jn_traj_expand``,
 ``jn_local_boxes`` and the K1 gathers, all on torch's current stream.
@@ -104,7 +104,7 @@ _det_capacity: Dict[tuple, int] = {}  # high-water mark of detection tiles per b
 
 
 def native_supported(rows: np.ndarray, cols: np.ndarray, exact_boxes: bool, seeds) -> bool:
-    if not exact_boxes or (len(rows) and (int(rows.max()) > 60 or int(cols.max()) > 60)):
+    if not exact_boxes or (len(rows) and (int(rows.max()) > 4096 or int(cols.max()) > 4096)):
         return False
     if seeds is not None:
         for s in seeds:
@@ -360,7 +360,7 @@ def plan_batch(bboxes: Sequence[Sequence], heights: Sequence[int], widths: Seque
         raise ValueError(f"unknown planner {planner!r}")
     use_native = planner != "python" and native_supported(rows, cols, exact, seeds)
     if planner == "native" and not use_native:
-        raise ValueError("the native planner needs integer boxes, grids up to 60x60 and seeds below 2**64")
+        raise ValueError("the native planner needs integer boxes, grids up to 4096x4096 and seeds below 2**64")
     if use_native:
         ticket = plan_native_start(boxes, n_boxes, n_max, rows, cols, patch_size, seeds, min_keypoints, max_keypoints,
                                    binomial_keypoints, position)

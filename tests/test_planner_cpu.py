@@ -250,3 +250,36 @@ def test_native_planner_on_its_own_thread_matches_the_blocking_call():
         finish()
     again = tj.plan_batch(bboxes, heights, widths, P, 0, 3, True, None, seeds, planner="native")  # usable again
     assert again.n == want.n
+
+
+def test_native_planner_wide_grids_follow_numpy_btpe():
+    """Grids wider than 60 patches: numpy's binomial switches from inversion to BTPE at n*p > 30; the native
+    planner restates both.  Around the switch (55..70) and far above it, against the planner that calls numpy."""
+    import random
+
+    from jolineedle_b200.env.trajectories import plan_batch
+
+    rng = np.random.default_rng(77)
+    segments = 0
+    for it in range(24):
+        n, P = int(rng.integers(1, 5)), 16
+        heights, widths, bboxes = [], [], []
+        for _ in range(n):
+            lo, hi = ((55, 70) if it % 2 else (61, 300))
+            gh, gw = int(rng.integers(lo, hi)), int(rng.integers(lo, hi))
+            boxes = []
+            for _ in range(int(rng.integers(0, 4))):
+                bw, bh = (int(v) for v in rng.integers(1, 3 * P, size=2))
+                x1, y1 = int(rng.integers(0, gw * P)), int(rng.integers(0, gh * P))
+                boxes.append(BBox(Position(y1, x1), Position(y1 + bh, x1 + bw)))
+            heights.append(gh * P); widths.append(gw * P); bboxes.append(boxes)
+        seeds = [int(s) for s in rng.integers(0, 2**63, size=n)]
+        random.seed(it)
+        py = plan_batch(bboxes, heights, widths, P, 2, 6, True, None, seeds, planner="python")
+        state_py = random.getstate()
+        random.seed(it)
+        nat = plan_batch(bboxes, heights, widths, P, 2, 6, True, None, seeds, planner="native")
+        assert random.getstate() == state_py
+        _assert_same_plans(py, nat)
+        segments += len(py.seg_flags)
+    assert segments > 500
