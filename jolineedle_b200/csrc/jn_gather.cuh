@@ -1,22 +1,23 @@
-// K1 -- the glimpse gather.  Three engines behind one argument block:
+// K1 -- the glimpse gather.  Four kernels behind one argument block:
 //
 //   copy   kernel: same dtype, plain [C,P,P] layout.  Pure DMA: one warp per CTA drives a
 //                  ring of shared-memory stages, TMA loads (tensor-map tiles or per-row bulk
 //                  copies) in, one TMA bulk store per stage out.  No thread touches a pixel.
-//   xform  kernel: uint8 -> float32 normalisation and / or the Focus space-to-depth layout.
-//                  Warp 0 is the TMA producer, the other warps read the staged tile from
-//                  shared memory, convert, and write coalesced vector stores.
+//                  Chunks are dealt round-robin to a persistent grid (q = blockIdx.x + j * gridDim.x).
+//   xform  kernel: uint8 -> float32 normalisation, the Focus space-to-depth layout, translated
+//                  and / or virtually padded sources.  Warp 0 is the TMA producer: it claims
+//                  chunks from a global counter, decodes 32 of them in parallel (one per lane) a
+//                  batch ahead, and hands every stage a descriptor through shared memory; the
+//                  other warps read the staged chunk, convert, and write coalesced vector stores.
 //   rows   kernel: plain loads, one warp per tile row: what the TMA unit cannot address --
-//                  source rows that do not start on a 16-byte boundary (arbitrary integer
-//                  translation), lists of images combined with a translation.
+//                  lists of images combined with a translation or padding, uint8 -> uint8 copies
+//                  with unaligned offsets.
 //   ldg    kernel: element-wise last resort (patch sizes that are not multiples of 4, outputs
 //                  that are not 16-byte aligned); with the rows kernel it is the "ldg" engine
 //                  and the in-GPU cross-check of the TMA engines in the tests.
 //
 // Work decomposition: a *chunk* is `rows` consecutive rows of one channel of one tile
-// (rows * P * elem bytes, contiguous in the plain output).  Chunks are dealt round-robin to
-// a persistent grid (q = blockIdx.x + j * gridDim.x), so neighbouring SMs stream
-// neighbouring rows of the same tile.
+// (rows * P * elem bytes, contiguous in the plain output).
 #pragma once
 
 #include "jn_device.cuh"
