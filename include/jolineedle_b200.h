@@ -67,6 +67,11 @@ typedef enum jn_overlap_rule {
 
 int jn_abi_version(void);
 const char* jn_last_error(void);
+/* Kernels launched by the library since it was loaded (all entry points, all threads). */
+long long jn_launch_count(void);
+/* First 16 hex digits of the SHA-256 of the native sources this library was built from (csrc/Makefile);
+ * profiles are stamped with it. */
+const char* jn_source_hash(void);
 /* SM count and compute capability of the current device. */
 int jn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 static inline int jn_bitmap_words(int rows, int cols) { return (rows * cols + 31) / 32; }
@@ -137,6 +142,9 @@ int jn_images_tma_ok(const jn_images* set, int engine /*jn_engine*/);
  * every row and realigns it in shared memory; same-dtype uint8 copies need JN_GATHER_SHIFT_ALIGNED and
  * P <= 256).  Lists of images: plain-load kernel (one warp per tile row).
  *
+ * `positions` may be NULL: patch (0, 0) of every item's image (sets of one-patch images, e.g. a crop
+ * history registered as an image set).
+ *
  * `status` (device int32[1], may be NULL) is OR-ed with 1 if some position was outside the
  * patch grid (that tile is skipped).
  * ------------------------------------------------------------------------------------------ */
@@ -155,6 +163,14 @@ int jn_patch_bitmaps(const int64_t* bboxes, const int32_t* n_boxes, int n, int m
                      int patch_size, int grid_rows, int grid_cols, const int32_t* rows,
                      const int32_t* cols, int rule /*jn_overlap_rule*/, uint32_t* out,
                      int words_per_item, void* stream);
+/* The same for boxes that are not whole pixels (float64 x1, y1, x2, y2; JN_RULE_AREA5 only): the dataset's
+ * minimum-size resize scales the boxes (dataset.py:258-270) and NeedleSimpleEnv keeps them as python floats;
+ * patch ranges floor(v / P), `oh * ow / P**2 > 0.05` and the centre floor((a + b) / 2) are evaluated in IEEE
+ * doubles like the reference's float arithmetic (simple_env.py:13-18,270-321). */
+int jn_patch_bitmaps_f64(const double* bboxes, const int32_t* n_boxes, int n, int max_boxes,
+                         int patch_size, int grid_rows, int grid_cols, const int32_t* rows,
+                         const int32_t* cols, int rule /*jn_overlap_rule*/, uint32_t* out,
+                         int words_per_item, void* stream);
 /* uint32 bitmaps -> one byte per patch, [n, rows, cols] (the reference's bool tensors). */
 int jn_bitmap_unpack(const uint32_t* words, int n, int rows, int cols, uint8_t* out, void* stream);
 /* Per-patch split of each box: local int64 [n, rows, cols, max_boxes, 4] (inclusive local
@@ -171,8 +187,14 @@ int jn_local_boxes(const int64_t* bboxes, const int32_t* n_boxes, int max_boxes,
                    const int64_t* positions, const int32_t* src_index, int n_items, float* out,
                    void* stream);
 
+/* float64 boxes: differences in double, rounded to float32 once (python floats into a FloatTensor). */
+int jn_local_boxes_f64(const double* bboxes, const int32_t* n_boxes, int max_boxes, int patch_size,
+                       const int64_t* positions, const int32_t* src_index, int n_items, float* out,
+                       void* stream);
+
 /* ------------------------------------------------------------------------------------------
- * K2  batched env reset / step (one warp per episode).
+ * K2  batched env reset / step (a warp per 32 episodes: lane per episode for the scalar state, groups of
+ * lanes over the bitmap words).
  * ------------------------------------------------------------------------------------------ */
 /* Clears visited / steps / has_stopped and marks the start patch.  Replaces
  * init_env_variables + the tail of reset (general_env.py:117-142,164). */
@@ -197,6 +219,55 @@ int jn_env_rewards(const int64_t* positions, const uint32_t* visited, const uint
 int jn_env_props(const uint32_t* visited, const uint32_t* bbox, const uint8_t* has_stopped, int n,
                  int rows, int cols, int stop_enabled, float* prop_patches, uint8_t* terminated,
                  void* stream);
+
+/* One call per env step: K2 followed by K1 without returning to the host language in between
+ * (general_env.py:172-207 `step`, :144-170 `reset`).
+ *
+ * jn_env_step_gather launches the step kernel (as jn_env_step) and, behind it with programmatic dependent
+ * launch, the gather of the new glimpses: tile (pos_out[i]) of image i -> out + i * out_item_stride_bytes.
+ * The gather does not wait for the step kernel: it moves pos_in by the action itself (same move + clamp),
+ * so both kernels run side by side and a step costs one launch latency.  pos_in and pos_out must not
+ * alias.  `set` NULL or `out` NULL: state update only.
+ *
+ * With a first-visit table (first_slot / host_src / history_src non-NULL; images in pinned HOST memory, crops
+ * kept in a history buffer of `slots` slots per episode, `t` = the slot being written) the step kernel also
+ * does the work of jn_visit_sources, the gather waits for it and reads only first visits from `set`, and a
+ * second gather copies revisited patches out of `history_set` (the history registered as n * slots
+ * one-patch images).  `host_tiles` (device uint64[1] or NULL) accumulates the number of first visits.
+ *
+ * jn_env_reset_gather: pos_out holds the start positions; clears the state (as jn_env_reset), initialises the
+ * first-visit table when there is one (slot 0), gathers slot 0. */
+typedef struct jn_env_step_args {
+  /* episode state, borrowed device pointers */
+  const int64_t* pos_in;  /* [n, 2] before the move (unused by reset) */
+  const int64_t* actions; /* [n] */
+  int64_t* pos_out;       /* [n, 2] after the move */
+  uint32_t* visited;      /* [n, words] */
+  const uint32_t* bbox;   /* [n, words] */
+  int64_t* steps;         /* [n] */
+  uint8_t* has_stopped;   /* [n] */
+  float* rewards;         /* [n] */
+  uint8_t* terminated;    /* [n] */
+  uint8_t* truncated;     /* [n] */
+  int32_t* first_slot;    /* [n, rows*cols] or NULL */
+  int32_t* host_src;      /* [n] or NULL */
+  int32_t* history_src;   /* [n] or NULL */
+  unsigned long long* host_tiles; /* [1] or NULL */
+  int32_t* status;        /* [1] or NULL: bit 1 bad position, bit 2 bad action */
+  int32_t n, rows, cols, max_ep_len, stop_enabled, slots, t;
+  float cost;             /* host-rounded float32 of -1 / max_ep_len */
+  /* gather of the new glimpses (see jn_gather) */
+  const int32_t* shifts;  /* [n_images, 2] or NULL */
+  void* out;
+  int64_t out_item_stride_bytes;
+  uint32_t flags;
+  int32_t engine;
+} jn_env_step_args;
+
+int jn_env_step_gather(const jn_images* set, const jn_images* history_set, const jn_env_step_args* args,
+                       void* stream);
+int jn_env_reset_gather(const jn_images* set, const jn_images* history_set, const jn_env_step_args* args,
+                        void* stream);
 
 /* Where this step's glimpse of every episode comes from when the images live in pinned HOST memory and the
  * crops are kept in a [n, slots, C, P, P] history buffer (NeedleGeneralEnv(history=True), the in-place form

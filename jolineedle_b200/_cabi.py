@@ -5,7 +5,7 @@ shared object is missing or a call fails, an exception is raised.
 """
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_longlong, c_uint32, c_void_p
 from typing import Optional
 
 import torch
@@ -31,9 +31,29 @@ class NativeLibraryError(RuntimeError):
 
 # name -> (restype, argtypes); one entry per symbol declared in include/jolineedle_b200.h
 _P = c_void_p
+
+
+class EnvStepArgs(ctypes.Structure):
+    """``jn_env_step_args`` of the header: borrowed device pointers of one env + the gather of its new glimpses.
+    An env fills it once and rewrites the handful of per-step fields before every call."""
+
+    _fields_ = [
+        ("pos_in", _P), ("actions", _P), ("pos_out", _P), ("visited", _P), ("bbox", _P), ("steps", _P),
+        ("has_stopped", _P), ("rewards", _P), ("terminated", _P), ("truncated", _P), ("first_slot", _P),
+        ("host_src", _P), ("history_src", _P), ("host_tiles", _P), ("status", _P),
+        ("n", c_int32), ("rows", c_int32), ("cols", c_int32), ("max_ep_len", c_int32), ("stop_enabled", c_int32),
+        ("slots", c_int32), ("t", c_int32), ("cost", c_float),
+        ("shifts", _P), ("out", _P), ("out_item_stride_bytes", c_int64), ("flags", c_uint32), ("engine", c_int32),
+    ]
+
+
 SIGNATURES = {
     "jn_abi_version": (c_int, []),
     "jn_last_error": (c_char_p, []),
+    "jn_launch_count": (c_longlong, []),
+    "jn_source_hash": (c_char_p, []),
+    "jn_env_step_gather": (c_int, [_P, _P, POINTER(EnvStepArgs), _P]),
+    "jn_env_reset_gather": (c_int, [_P, _P, POINTER(EnvStepArgs), _P]),
     "jn_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "jn_selftest_host": (c_int, [POINTER(c_float), POINTER(c_int)]),
     "jn_images_create": (c_int, [POINTER(_P), c_int, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
@@ -42,6 +62,8 @@ SIGNATURES = {
     "jn_images_tma_ok": (c_int, [_P, c_int]),
     "jn_gather": (c_int, [_P, _P, _P, _P, c_int, _P, c_int64, c_uint32, c_int, _P, _P]),
     "jn_patch_bitmaps": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, _P]),
+    "jn_patch_bitmaps_f64": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, _P]),
+    "jn_local_boxes_f64": (c_int, [_P, _P, c_int, c_int, _P, _P, c_int, _P, _P]),
     "jn_bitmap_unpack": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "jn_split_boxes": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "jn_local_boxes": (c_int, [_P, _P, c_int, c_int, _P, _P, c_int, _P, _P]),
@@ -67,43 +89,14 @@ SIGNATURES = {
     "jn_plan_export": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 
-# entry points that launch exactly one kernel of ours per successful call
-KERNEL_CALLS = frozenset({
-    "jn_gather", "jn_patch_bitmaps", "jn_bitmap_unpack", "jn_split_boxes", "jn_local_boxes", "jn_env_reset",
-    "jn_env_step", "jn_env_props", "jn_env_rewards", "jn_tile_lookup", "jn_tile_dedupe", "jn_visit_sources", "jn_returns", "jn_returns_rows", "jn_traj_expand",
-})
-
-
-class _CountingLibrary:
-    """Attribute proxy over the CDLL that counts kernel-launching calls (bench.py reports the
-    number of our launches inside its timed region)."""
-
-    def __init__(self, handle: ctypes.CDLL):
-        self._handle = handle
-        self.launches = 0
-        for name in SIGNATURES:
-            fn = getattr(handle, name)
-            if name in KERNEL_CALLS:
-                setattr(self, name, self._counted(fn))
-            else:
-                setattr(self, name, fn)
-
-    def _counted(self, fn):
-        def call(*args):
-            self.launches += 1
-            return fn(*args)
-
-        return call
-
-
-_lib: Optional[_CountingLibrary] = None
+_lib: Optional[ctypes.CDLL] = None
 
 
 def library_path() -> str:
     return _LIB_PATH
 
 
-def lib() -> _CountingLibrary:
+def lib() -> ctypes.CDLL:
     """Load the shared object (once).  Raises ``NativeLibraryError`` when it is not built."""
     global _lib
     if _lib is None:
@@ -119,13 +112,13 @@ def lib() -> _CountingLibrary:
             fn.argtypes = argtypes
         if handle.jn_abi_version() != 1:
             raise NativeLibraryError(f"ABI version mismatch: library reports {handle.jn_abi_version()}")
-        _lib = _CountingLibrary(handle)
+        _lib = handle
     return _lib
 
 
 def launch_count() -> int:
-    """Kernel launches issued through this binding since import."""
-    return lib().launches
+    """Kernels launched by the library since it was loaded (counted at the launch sites, in C)."""
+    return int(lib().jn_launch_count())
 
 
 def check(rc: int, invalid_exc=ValueError):

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -18,6 +19,8 @@
 namespace {
 
 thread_local char g_error[512] = "";
+// Kernel launches issued by this library since it was loaded (bench.py reports the launches of its timed region).
+std::atomic<long long> g_launches{0};
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -32,6 +35,12 @@ int fail(int code, const char* fmt, ...) {
     cudaError_t err__ = (expr);                                                                    \
     if (err__ != cudaSuccess)                                                                      \
       return fail(JN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+  } while (0)
+
+#define JN_LAUNCHED()                                      \
+  do {                                                     \
+    g_launches.fetch_add(1, std::memory_order_relaxed);    \
+    JN_CUDA(cudaGetLastError());                           \
   } while (0)
 
 #define JN_REQUIRE(cond, ...)                              \
@@ -99,6 +108,24 @@ int* next_work_counter(int device) {
   return base;
 }
 
+// One launch through cudaLaunchKernelEx; `pdl` adds the programmatic-stream-serialization attribute: the kernel
+// may start while the previous kernel of the stream is still running (after that one's
+// griddepcontrol.launch_dependents), and orders itself with griddepcontrol.wait where it needs to.
+template <typename... Params, typename... Args>
+cudaError_t launch_kernel(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (pdl) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
+
 inline int grid_for(long long work_items, int per_block, int cap) {
   long long g = (work_items + per_block - 1) / per_block;
   if (g < 1) g = 1;
@@ -122,8 +149,11 @@ struct jn_images {
   // engines
   bool bulk_ok = false, tensor_ok = false;
   int box_w = 0, kbox = 0;
-  CUtensorMap map0;
   int device = 0;
+  // tensor maps by chunk geometry, encoded on first use (see cached_map)
+  struct CachedMap { int kind, rows, pitch; CUtensorMap map; };
+  mutable std::mutex mu;
+  mutable std::vector<CachedMap> maps;
 };
 
 namespace {
@@ -246,18 +276,39 @@ GatherTune gather_tune(int patch, int elem, bool plain_copy, bool focus, int eng
   return t;
 }
 
+// Resident CTAs per SM of a persistent gather kernel at a given shared-memory size: asked of the runtime once
+// per (kernel, size, device) -- cudaFuncSetAttribute + the occupancy query cost ~3 us per launch otherwise,
+// which matters for the 256-tile launches of the batched env.
+template <typename Kernel>
+int persistent_ctas_per_sm(Kernel kernel, int threads, size_t smem, int device, int* per_sm) {
+  struct Entry { const void* fn; size_t smem; int device, per_sm; };
+  static std::mutex mu;
+  static std::vector<Entry> cache;
+  const void* fn = reinterpret_cast<const void*>(kernel);
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    for (const auto& e : cache)
+      if (e.fn == fn && e.smem == smem && e.device == device) { *per_sm = e.per_sm; return JN_OK; }
+  }
+  JN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int n = 0;
+  JN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem));
+  std::lock_guard<std::mutex> lock(mu);
+  cache.push_back({fn, smem, device, n});
+  *per_sm = n;
+  return JN_OK;
+}
+
 template <typename Kernel, typename... Extra>
 int launch_persistent(Kernel kernel, const jnk::GatherArgs& a, const CUtensorMap& map, int threads, size_t smem,
-                      const DeviceInfo& dev, cudaStream_t stream, int ctas_cap, Extra... extra) {
-  JN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                      const DeviceInfo& dev, cudaStream_t stream, int ctas_cap, bool pdl, Extra... extra) {
   int per_sm = 0;
-  JN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+  if (int rc = persistent_ctas_per_sm(kernel, threads, smem, dev.device, &per_sm)) return rc;
   if (per_sm < 1) return fail(JN_ERR_CUDA, "gather kernel does not fit on an SM (%zu bytes of shared memory)", smem);
   if (ctas_cap > 0 && per_sm > ctas_cap) per_sm = ctas_cap;
   long long grid = (long long)dev.sm_count * per_sm;
   if (grid > a.total_chunks) grid = a.total_chunks;
-  kernel<<<(int)grid, threads, smem, stream>>>(a, map, extra...);
-  JN_CUDA(cudaGetLastError());
+  JN_CUDA(launch_kernel(kernel, dim3((unsigned)grid), dim3((unsigned)threads), smem, stream, pdl, a, map, extra...));
   return JN_OK;
 }
 
@@ -325,7 +376,6 @@ static int images_create(jn_images** out, int n_slabs, const void* const* slab_p
   s->box_w = aligned ? pick_box_width(patch_size, elem) : 0;
   s->kbox = s->box_w ? patch_size / s->box_w : 0;
   s->tensor_ok = aligned && s->box_w > 0 && encode_tiled_fn() != nullptr;
-  memset(&s->map0, 0, sizeof(s->map0));
 
   auto bail = [&](int rc) { jn_images_destroy(s); return rc; };
   if (n_slabs == 1) {
@@ -392,14 +442,61 @@ int jn_images_tma_ok(const jn_images* s, int engine) {
 // ------------------------------------------------------------------------------------------
 // K1 gather
 // ------------------------------------------------------------------------------------------
-int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src_index, const int32_t* shifts,
-              int n_items, void* out, int64_t out_item_stride_bytes, uint32_t flags, int engine, int32_t* status,
-              void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+}  // extern "C"
+
+namespace {
+
+// What a gather is asked to do: the arguments of jn_gather plus the fused-step extras of jn_env_step_gather.
+struct GatherRequest {
+  const int64_t* positions = nullptr;
+  const int32_t* src_index = nullptr;
+  const int32_t* shifts = nullptr;
+  int n_items = 0;
+  void* out = nullptr;
+  int64_t out_item_stride_bytes = 0;
+  uint32_t flags = 0;
+  int engine = JN_ENGINE_AUTO;
+  int32_t* status = nullptr;
+  const int64_t* actions = nullptr;  // fused step: positions are pre-move, the kernel applies the action itself
+  int grid_rows = 0, grid_cols = 0;
+  bool pdl = false;         // launch with the programmatic-serialization attribute (behind the step kernel)
+  bool wait_prior = false;  // ... and wait for that kernel before the first index load
+};
+
+// Tensor map of an image set for one chunk geometry; encoded once and kept with the set
+// (cuTensorMapEncodeTiled costs a few microseconds, as much as the launch of a small gather).
+int cached_map(const jn_images* set, int kind /*0 tiled 4-D, 1 tiled 3-D, 2 superset rows*/, int rows, int pitch,
+               CUtensorMap* out) {
+  std::lock_guard<std::mutex> lock(set->mu);
+  for (const auto& m : set->maps)
+    if (m.kind == kind && m.rows == rows && m.pitch == pitch) { *out = m.map; return JN_OK; }
+  jn_images::CachedMap m;
+  m.kind = kind; m.rows = rows; m.pitch = pitch;
+  memset(&m.map, 0, sizeof(m.map));
+  const int planes = set->n_images * set->channels;
+  if (int rc = kind == 2 ? encode_shift_map(&m.map, set->base, set->elem, planes, set->height, set->width, pitch, rows)
+                         : encode_slab_map(&m.map, set->base, set->elem, planes, set->height, set->width, set->box_w,
+                                           set->kbox, rows, kind == 1))
+    return rc;
+  set->maps.push_back(m);
+  *out = m.map;
+  return JN_OK;
+}
+
+int gather_launch(const jn_images* set, const GatherRequest& rq, cudaStream_t stream) {
+  const int64_t* positions = rq.positions;
+  const int32_t *src_index = rq.src_index, *shifts = rq.shifts;
+  const int n_items = rq.n_items;
+  void* out = rq.out;
+  const int64_t out_item_stride_bytes = rq.out_item_stride_bytes;
+  const uint32_t flags = rq.flags;
+  int engine = rq.engine;
+  int32_t* status = rq.status;
   JN_REQUIRE(set != nullptr, "jn_gather: image set is NULL");
   JN_REQUIRE(n_items >= 0, "jn_gather: negative item count");
   if (n_items == 0) return JN_OK;
-  JN_REQUIRE(positions != nullptr && out != nullptr, "jn_gather: NULL positions / out");
+  JN_REQUIRE(out != nullptr, "jn_gather: NULL out");
+  JN_REQUIRE(positions != nullptr || rq.actions == nullptr, "jn_gather: actions without positions");
   const bool normalize = (flags & JN_GATHER_NORMALIZE) != 0, focus = (flags & JN_GATHER_FOCUS) != 0;
   JN_REQUIRE(!(normalize && set->dtype != JN_U8), "JN_GATHER_NORMALIZE needs a uint8 image set");
   JN_REQUIRE(!(focus && (set->patch % 2)), "JN_GATHER_FOCUS needs an even patch size");
@@ -423,6 +520,8 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
   a.box_w = set->box_w; a.kbox = set->kbox;
   a.skip_negative = (flags & JN_GATHER_SKIP_NEGATIVE) ? 1 : 0;
   a.padded = set->padded ? 1 : 0;
+  a.actions = rq.actions; a.grid_rows = rq.grid_rows; a.grid_cols = rq.grid_cols;
+  a.wait_prior = rq.wait_prior ? 1 : 0;
 
   const bool plain_copy = !normalize && !focus;
   const bool out_aligned = reinterpret_cast<uintptr_t>(out) % 16 == 0 && out_item_stride_bytes % 16 == 0;
@@ -473,14 +572,13 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
     const bool rows_ok = P % 4 == 0 && out_aligned && !(focus && out_elem == 1);
     if (rows_ok) {  // one warp per tile row, 16-byte stores
       const long long units = (long long)n_items * C * P;
-      jnk::gather_rows_kernel<<<grid_for(units, 8, dev.sm_count * 8), 256, 0, stream>>>(a, out_elem == 4, normalize,
-                                                                                         focus);
+      JN_CUDA(launch_kernel(jnk::gather_rows_kernel, dim3(grid_for(units, 8, dev.sm_count * 8)), dim3(256), 0, stream,
+                            rq.pdl, a, out_elem == 4 ? 1 : 0, normalize ? 1 : 0, focus ? 1 : 0));
     } else {  // any patch size / alignment: one thread per element
       const long long total = (long long)n_items * C * P * P;
-      jnk::gather_ldg_kernel<<<grid_for(total, 256 * 8, dev.sm_count * 16), 256, 0, stream>>>(a, out_elem == 4,
-                                                                                               normalize, focus);
+      JN_CUDA(launch_kernel(jnk::gather_ldg_kernel, dim3(grid_for(total, 256 * 8, dev.sm_count * 16)), dim3(256), 0,
+                            stream, rq.pdl, a, out_elem == 4 ? 1 : 0, normalize ? 1 : 0, focus ? 1 : 0));
     }
-    JN_CUDA(cudaGetLastError());
     return JN_OK;
   }
 
@@ -506,10 +604,7 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   if (engine == JN_ENGINE_TENSOR) {
-    if (int rc = shift_xform ? encode_shift_map(&map, set->base, set->elem, set->n_images * C, set->height, set->width,
-                                                a.pitch, rows)
-                             : encode_slab_map(&map, set->base, set->elem, set->n_images * C, set->height, set->width,
-                                               set->box_w, set->kbox, rows, shifts != nullptr))
+    if (int rc = cached_map(set, shift_xform ? 2 : (shifts != nullptr ? 1 : 0), rows, shift_xform ? a.pitch : 0, &map))
       return rc;
   }
 
@@ -518,8 +613,10 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
     const bool tensor = engine == JN_ENGINE_TENSOR;
 #define JN_COPY(S, D)                                                                                              \
   if (tune.copy_stages == S && tune.copy_ahead == D)                                                               \
-    return tensor ? launch_persistent(jnk::gather_copy_kernel<S, D, true>, a, map, 32, smem, dev, stream, tune.copy_ctas) \
-                  : launch_persistent(jnk::gather_copy_kernel<S, D, false>, a, map, 32, smem, dev, stream, tune.copy_ctas);
+    return tensor ? launch_persistent(jnk::gather_copy_kernel<S, D, true>, a, map, 32, smem, dev, stream,          \
+                                      tune.copy_ctas, rq.pdl)                                                       \
+                  : launch_persistent(jnk::gather_copy_kernel<S, D, false>, a, map, 32, smem, dev, stream,         \
+                                      tune.copy_ctas, rq.pdl);
     JN_COPY(6, 3) JN_COPY(2, 1) JN_COPY(3, 1) JN_COPY(3, 2) JN_COPY(4, 1) JN_COPY(4, 2) JN_COPY(4, 3) JN_COPY(6, 2)
     JN_COPY(6, 4) JN_COPY(6, 5) JN_COPY(8, 4) JN_COPY(8, 6) JN_COPY(12, 6) JN_COPY(12, 9)
 #undef JN_COPY
@@ -535,9 +632,9 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
              a.stage_bytes);
 #define JN_XFORM(mode)                                                                                             \
   return shift_xform ? launch_persistent(jnk::gather_xform_kernel<mode, kXformWarps, true>, a, map, threads, smem, \
-                                         dev, stream, tune.xform_ctas, stages, tensor)                             \
+                                         dev, stream, tune.xform_ctas, rq.pdl, stages, tensor)                     \
                      : launch_persistent(jnk::gather_xform_kernel<mode, kXformWarps, false>, a, map, threads, smem, \
-                                         dev, stream, tune.xform_ctas, stages, tensor);
+                                         dev, stream, tune.xform_ctas, rq.pdl, stages, tensor);
   if (normalize && !focus) { JN_XFORM(jnk::kNormPlain) }
   else if (normalize && focus) { JN_XFORM(jnk::kNormFocus) }
   else if (focus) { JN_XFORM(jnk::kF32Focus) }
@@ -545,26 +642,93 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
 #undef JN_XFORM
 }
 
+}  // namespace
+
+extern "C" {
+
+int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src_index, const int32_t* shifts,
+              int n_items, void* out, int64_t out_item_stride_bytes, uint32_t flags, int engine, int32_t* status,
+              void* stream) {
+  GatherRequest rq;
+  rq.positions = positions; rq.src_index = src_index; rq.shifts = shifts; rq.n_items = n_items; rq.out = out;
+  rq.out_item_stride_bytes = out_item_stride_bytes; rq.flags = flags; rq.engine = engine; rq.status = status;
+  return gather_launch(set, rq, (cudaStream_t)stream);
+}
+
+long long jn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+#ifndef JN_SOURCE_HASH
+#define JN_SOURCE_HASH "unknown"
+#endif
+const char* jn_source_hash(void) { return JN_SOURCE_HASH; }
+
 // ------------------------------------------------------------------------------------------
 // K0 tables
 // ------------------------------------------------------------------------------------------
-int jn_patch_bitmaps(const int64_t* bboxes, const int32_t* n_boxes, int n, int max_boxes, int patch_size,
-                     int grid_rows, int grid_cols, const int32_t* rows, const int32_t* cols, int rule, uint32_t* out,
-                     int words_per_item, void* stream) {
+}  // extern "C"
+
+namespace {
+
+int patch_bitmaps(const void* bboxes, bool f64, const int32_t* n_boxes, int n, int max_boxes, int patch_size,
+                  int grid_rows, int grid_cols, const int32_t* rows, const int32_t* cols, int rule, uint32_t* out,
+                  int words_per_item, void* stream) {
   JN_REQUIRE(n >= 0 && max_boxes >= 0 && patch_size >= 1, "jn_patch_bitmaps: bad sizes");
   if (n == 0) return JN_OK;
   JN_REQUIRE(out != nullptr && (bboxes != nullptr || max_boxes == 0), "jn_patch_bitmaps: NULL pointer");
   JN_REQUIRE(rule == JN_RULE_ANY_PIXEL || rule == JN_RULE_AREA5, "jn_patch_bitmaps: unknown rule %d", rule);
+  JN_REQUIRE(!f64 || rule == JN_RULE_AREA5, "jn_patch_bitmaps_f64 serves JN_RULE_AREA5 only");
   JN_REQUIRE((rows && cols) || (grid_rows >= 1 && grid_cols >= 1), "jn_patch_bitmaps: grid size missing");
   JN_REQUIRE((rows && cols) ? words_per_item >= 1 : words_per_item >= jn_bitmap_words(grid_rows, grid_cols),
              "jn_patch_bitmaps: words_per_item too small");
   DeviceInfo dev;
   if (int rc = current_device_info(dev)) return rc;
   const int wpb = 4;
-  jnk::patch_bitmaps_kernel<<<grid_for(n, wpb, dev.sm_count * 8), wpb * 32, 0, (cudaStream_t)stream>>>(
-      bboxes, n_boxes, n, max_boxes, patch_size, grid_rows, grid_cols, rows, cols, rule, out, words_per_item);
-  JN_CUDA(cudaGetLastError());
+  const dim3 grid(grid_for(n, wpb, dev.sm_count * 8)), block(wpb * 32);
+  if (f64)
+    jnk::patch_bitmaps_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(
+        bboxes, n_boxes, n, max_boxes, patch_size, grid_rows, grid_cols, rows, cols, rule, out, words_per_item);
+  else
+    jnk::patch_bitmaps_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(
+        bboxes, n_boxes, n, max_boxes, patch_size, grid_rows, grid_cols, rows, cols, rule, out, words_per_item);
+  JN_LAUNCHED();
   return JN_OK;
+}
+
+int local_boxes(const void* bboxes, bool f64, const int32_t* n_boxes, int max_boxes, int patch_size,
+                const int64_t* positions, const int32_t* src_index, int n_items, float* out, void* stream) {
+  JN_REQUIRE(n_items >= 0 && max_boxes >= 0 && patch_size >= 1, "jn_local_boxes: bad sizes");
+  const long long total = (long long)n_items * max_boxes;
+  if (total == 0) return JN_OK;
+  JN_REQUIRE(bboxes && positions && out, "jn_local_boxes: NULL pointer");
+  DeviceInfo dev;
+  if (int rc = current_device_info(dev)) return rc;
+  const dim3 grid(grid_for(total, 256, dev.sm_count * 8)), block(256);
+  if (f64)
+    jnk::local_boxes_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(bboxes, n_boxes, max_boxes, patch_size,
+                                                                          positions, src_index, n_items, out);
+  else
+    jnk::local_boxes_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(bboxes, n_boxes, max_boxes, patch_size,
+                                                                           positions, src_index, n_items, out);
+  JN_LAUNCHED();
+  return JN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int jn_patch_bitmaps(const int64_t* bboxes, const int32_t* n_boxes, int n, int max_boxes, int patch_size,
+                     int grid_rows, int grid_cols, const int32_t* rows, const int32_t* cols, int rule, uint32_t* out,
+                     int words_per_item, void* stream) {
+  return patch_bitmaps(bboxes, false, n_boxes, n, max_boxes, patch_size, grid_rows, grid_cols, rows, cols, rule, out,
+                       words_per_item, stream);
+}
+
+int jn_patch_bitmaps_f64(const double* bboxes, const int32_t* n_boxes, int n, int max_boxes, int patch_size,
+                         int grid_rows, int grid_cols, const int32_t* rows, const int32_t* cols, int rule,
+                         uint32_t* out, int words_per_item, void* stream) {
+  return patch_bitmaps(bboxes, true, n_boxes, n, max_boxes, patch_size, grid_rows, grid_cols, rows, cols, rule, out,
+                       words_per_item, stream);
 }
 
 int jn_bitmap_unpack(const uint32_t* words, int n, int rows, int cols, uint8_t* out, void* stream) {
@@ -576,7 +740,7 @@ int jn_bitmap_unpack(const uint32_t* words, int n, int rows, int cols, uint8_t* 
   const long long total = (long long)n * rows * cols;
   jnk::bitmap_unpack_kernel<<<grid_for(total, 256, dev.sm_count * 8), 256, 0, (cudaStream_t)stream>>>(
       words, n, rows * cols, jn_bitmap_words(rows, cols), out);
-  JN_CUDA(cudaGetLastError());
+  JN_LAUNCHED();
   return JN_OK;
 }
 
@@ -590,76 +754,155 @@ int jn_split_boxes(const int64_t* bboxes, int n, int max_boxes, int patch_size, 
   if (int rc = current_device_info(dev)) return rc;
   jnk::split_boxes_kernel<<<grid_for(total, 256, dev.sm_count * 8), 256, 0, (cudaStream_t)stream>>>(
       bboxes, n, max_boxes, patch_size, rows, cols, local, present, status);
-  JN_CUDA(cudaGetLastError());
+  JN_LAUNCHED();
   return JN_OK;
 }
 
 int jn_local_boxes(const int64_t* bboxes, const int32_t* n_boxes, int max_boxes, int patch_size,
                    const int64_t* positions, const int32_t* src_index, int n_items, float* out, void* stream) {
-  JN_REQUIRE(n_items >= 0 && max_boxes >= 0 && patch_size >= 1, "jn_local_boxes: bad sizes");
-  const long long total = (long long)n_items * max_boxes;
-  if (total == 0) return JN_OK;
-  JN_REQUIRE(bboxes && positions && out, "jn_local_boxes: NULL pointer");
-  DeviceInfo dev;
-  if (int rc = current_device_info(dev)) return rc;
-  jnk::local_boxes_kernel<<<grid_for(total, 256, dev.sm_count * 8), 256, 0, (cudaStream_t)stream>>>(
-      bboxes, n_boxes, max_boxes, patch_size, positions, src_index, n_items, out);
-  JN_CUDA(cudaGetLastError());
-  return JN_OK;
+  return local_boxes(bboxes, false, n_boxes, max_boxes, patch_size, positions, src_index, n_items, out, stream);
+}
+
+int jn_local_boxes_f64(const double* bboxes, const int32_t* n_boxes, int max_boxes, int patch_size,
+                       const int64_t* positions, const int32_t* src_index, int n_items, float* out, void* stream) {
+  return local_boxes(bboxes, true, n_boxes, max_boxes, patch_size, positions, src_index, n_items, out, stream);
 }
 
 // ------------------------------------------------------------------------------------------
 // K2 env
 // ------------------------------------------------------------------------------------------
-int jn_env_reset(const int64_t* positions, uint32_t* visited, int64_t* steps, uint8_t* has_stopped, int n, int rows,
-                 int cols, int32_t* status, void* stream) {
-  JN_REQUIRE(n >= 0 && rows >= 1 && cols >= 1, "jn_env_reset: bad sizes");
-  if (n == 0) return JN_OK;
-  JN_REQUIRE(positions && visited && steps && has_stopped, "jn_env_reset: NULL pointer");
+}  // extern "C"
+
+namespace {
+
+int check_step_args(const jn_env_step_args* p, bool stepping, const char* who) {
+  JN_REQUIRE(p != nullptr, "%s: args is NULL", who);
+  JN_REQUIRE(p->n >= 0 && p->rows >= 1 && p->cols >= 1 && p->max_ep_len >= 1, "%s: bad sizes", who);
+  JN_REQUIRE((long long)p->rows * p->cols <= 65535, "%s: grids of more than 65535 patches are not supported", who);
+  if (p->n == 0) return JN_OK;
+  JN_REQUIRE(p->pos_out && p->visited && p->steps && p->has_stopped, "%s: NULL state pointer", who);
+  if (stepping)
+    JN_REQUIRE(p->pos_in && p->actions && p->bbox && p->rewards && p->terminated && p->truncated,
+               "%s: NULL pointer", who);
+  if (p->first_slot) {
+    JN_REQUIRE(p->host_src && p->history_src, "%s: first_slot needs host_src and history_src", who);
+    JN_REQUIRE(p->slots >= 1 && p->t >= 0 && p->t < p->slots, "%s: history slot %d outside [0, %d)", who, p->t, p->slots);
+    JN_REQUIRE((long long)p->n * p->slots < (1ll << 31), "%s: history of %d x %d slots is too large", who, p->n, p->slots);
+  }
+  return JN_OK;
+}
+
+jnk::StepArgs to_step_args(const jn_env_step_args* p) {
+  jnk::StepArgs a;
+  a.pos_in = p->pos_in; a.actions = p->actions; a.pos_out = p->pos_out; a.visited = p->visited; a.bbox = p->bbox;
+  a.steps = p->steps; a.has_stopped = p->has_stopped; a.rewards = p->rewards; a.terminated = p->terminated;
+  a.truncated = p->truncated; a.first_slot = p->first_slot; a.host_src = p->host_src; a.history_src = p->history_src;
+  a.host_tiles = p->host_tiles; a.status = p->status;
+  a.n = p->n; a.rows = p->rows; a.cols = p->cols; a.words = jn_bitmap_words(p->rows, p->cols);
+  a.max_ep_len = p->max_ep_len; a.stop_enabled = p->stop_enabled; a.slots = p->slots; a.t = p->t; a.cost = p->cost;
+  return a;
+}
+
+int launch_reset(const jnk::StepArgs& a, cudaStream_t stream) {
   DeviceInfo dev;
   if (int rc = current_device_info(dev)) return rc;
-  const int wpb = 4;
-  jnk::env_reset_kernel<<<grid_for(n, wpb, dev.sm_count * 16), wpb * 32, 0, (cudaStream_t)stream>>>(
-      positions, visited, steps, has_stopped, n, rows, cols, jn_bitmap_words(rows, cols), status);
-  JN_CUDA(cudaGetLastError());
+  const long long cells = a.first_slot ? (long long)a.rows * a.cols : 0;
+  const long long total = (long long)a.n * (a.words > cells ? a.words : cells);
+  JN_CUDA(launch_kernel(jnk::env_reset_kernel, dim3(grid_for(total, 128, dev.sm_count * 16)), dim3(128), 0, stream,
+                        false, a));
   return JN_OK;
+}
+
+int launch_step(const jnk::StepArgs& a, cudaStream_t stream) {
+  DeviceInfo dev;
+  if (int rc = current_device_info(dev)) return rc;
+  // G lanes per episode in the bitmap phase: the power of two >= the number of bitmap words, at most a warp
+  int g = 1;
+  while (g < a.words && g < 32) g <<= 1;
+  const dim3 grid(grid_for(a.n, 64, dev.sm_count * 16)), block(64);  // a warp steps 32 episodes
+#define JN_STEP(G) \
+  case G: JN_CUDA(launch_kernel(jnk::env_step_kernel<G>, grid, block, 0, stream, false, a)); break;
+  switch (g) { JN_STEP(1) JN_STEP(2) JN_STEP(4) JN_STEP(8) JN_STEP(16) JN_STEP(32) }
+#undef JN_STEP
+  return JN_OK;
+}
+
+// The gather that follows a reset / step inside the same call.
+int gather_after(const jn_images* set, const jn_images* history_set, const jn_env_step_args* p, bool stepping,
+                 cudaStream_t stream) {
+  if (!set || !p->out) return JN_OK;  // state only
+  const bool zero_copy = p->first_slot != nullptr;
+  GatherRequest rq;
+  rq.shifts = p->shifts; rq.n_items = p->n; rq.out = p->out; rq.out_item_stride_bytes = p->out_item_stride_bytes;
+  rq.flags = p->flags; rq.engine = p->engine; rq.status = p->status;
+  rq.grid_rows = p->rows; rq.grid_cols = p->cols;
+  rq.pdl = true;
+  if (zero_copy) {
+    // sources come from the kernel before us: positions after the move, first visits only
+    rq.positions = p->pos_out; rq.src_index = p->host_src; rq.wait_prior = true;
+  } else if (stepping) {
+    // independent of the step kernel: the gather moves the old positions itself and runs next to it
+    rq.positions = p->pos_in; rq.actions = p->actions;
+  } else {
+    rq.positions = p->pos_out;  // reset: the start positions (the reset kernel does not write them)
+  }
+  if (int rc = gather_launch(set, rq, stream)) return rc;
+  if (zero_copy && history_set) {
+    // revisited patches: copied from the history slot that first held them (one-patch images, patch (0, 0))
+    GatherRequest rh;
+    rh.src_index = p->history_src; rh.n_items = p->n; rh.out = p->out;
+    rh.out_item_stride_bytes = p->out_item_stride_bytes; rh.flags = 0; rh.engine = p->engine; rh.status = p->status;
+    if (int rc = gather_launch(history_set, rh, stream)) return rc;
+  }
+  return JN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int jn_env_reset(const int64_t* positions, uint32_t* visited, int64_t* steps, uint8_t* has_stopped, int n, int rows,
+                 int cols, int32_t* status, void* stream) {
+  jn_env_step_args p;
+  memset(&p, 0, sizeof(p));
+  p.pos_out = const_cast<int64_t*>(positions); p.visited = visited; p.steps = steps; p.has_stopped = has_stopped;
+  p.n = n; p.rows = rows; p.cols = cols; p.max_ep_len = 1; p.status = status;
+  if (int rc = check_step_args(&p, false, "jn_env_reset")) return rc;
+  if (n == 0) return JN_OK;
+  return launch_reset(to_step_args(&p), (cudaStream_t)stream);
 }
 
 int jn_env_step(const int64_t* pos_in, const int64_t* actions, int64_t* pos_out, uint32_t* visited,
                 const uint32_t* bbox, int64_t* steps, uint8_t* has_stopped, float* rewards, uint8_t* terminated,
                 uint8_t* truncated, int n, int rows, int cols, int max_ep_len, float cost, int stop_enabled,
                 int32_t* status, void* stream) {
-  JN_REQUIRE(n >= 0 && rows >= 1 && cols >= 1 && max_ep_len >= 1, "jn_env_step: bad sizes");
+  jn_env_step_args p;
+  memset(&p, 0, sizeof(p));
+  p.pos_in = pos_in; p.actions = actions; p.pos_out = pos_out; p.visited = visited; p.bbox = bbox; p.steps = steps;
+  p.has_stopped = has_stopped; p.rewards = rewards; p.terminated = terminated; p.truncated = truncated;
+  p.n = n; p.rows = rows; p.cols = cols; p.max_ep_len = max_ep_len; p.cost = cost; p.stop_enabled = stop_enabled;
+  p.status = status;
+  if (int rc = check_step_args(&p, true, "jn_env_step")) return rc;
   if (n == 0) return JN_OK;
-  JN_REQUIRE(pos_in && actions && pos_out && visited && bbox && steps && has_stopped && rewards && terminated &&
-                 truncated,
-             "jn_env_step: NULL pointer");
-  DeviceInfo dev;
-  if (int rc = current_device_info(dev)) return rc;
-  const bool aligned16 = reinterpret_cast<uintptr_t>(pos_in) % 16 == 0 && reinterpret_cast<uintptr_t>(pos_out) % 16 == 0;
-  if (jn_bitmap_words(rows, cols) == 1 && aligned16 && pos_in != pos_out) {
-    // one-word bitmaps: a lane per episode keeps all 32 lanes of a warp busy
-    jnk::env_step_lane_kernel<<<grid_for(n, 128, dev.sm_count * 16), 128, 0, (cudaStream_t)stream>>>(
-        pos_in, actions, pos_out, visited, bbox, steps, has_stopped, rewards, terminated, truncated, n, rows, cols,
-        max_ep_len, cost, stop_enabled, status);
-    JN_CUDA(cudaGetLastError());
-    return JN_OK;
-  }
-  // groups of G lanes per episode, G = the power of two >= the number of bitmap words (at most a warp)
-  const int words = jn_bitmap_words(rows, cols), wpb = 4;
-  int g = 1;
-  while (g < words && g < 32) g <<= 1;
-  const int per_block = wpb * (32 / g);
-#define JN_STEP(G)                                                                                               \
-  case G:                                                                                                        \
-    jnk::env_step_group_kernel<G><<<grid_for(n, per_block, dev.sm_count * 16), wpb * 32, 0, (cudaStream_t)stream>>>( \
-        pos_in, actions, pos_out, visited, bbox, steps, has_stopped, rewards, terminated, truncated, n, rows, cols, \
-        words, max_ep_len, cost, stop_enabled, status);                                                          \
-    break;
-  switch (g) { JN_STEP(1) JN_STEP(2) JN_STEP(4) JN_STEP(8) JN_STEP(16) JN_STEP(32) }
-#undef JN_STEP
-  JN_CUDA(cudaGetLastError());
-  return JN_OK;
+  return launch_step(to_step_args(&p), (cudaStream_t)stream);
+}
+
+int jn_env_reset_gather(const jn_images* set, const jn_images* history_set, const jn_env_step_args* args,
+                        void* stream) {
+  if (int rc = check_step_args(args, false, "jn_env_reset_gather")) return rc;
+  if (args->n == 0) return JN_OK;
+  if (int rc = launch_reset(to_step_args(args), (cudaStream_t)stream)) return rc;
+  return gather_after(set, history_set, args, false, (cudaStream_t)stream);
+}
+
+int jn_env_step_gather(const jn_images* set, const jn_images* history_set, const jn_env_step_args* args,
+                       void* stream) {
+  if (int rc = check_step_args(args, true, "jn_env_step_gather")) return rc;
+  if (args->n == 0) return JN_OK;
+  JN_REQUIRE(args->pos_in != args->pos_out || !set || !args->out,
+             "jn_env_step_gather: pos_in and pos_out must not alias (the gather reads pos_in while the step runs)");
+  if (int rc = launch_step(to_step_args(args), (cudaStream_t)stream)) return rc;
+  return gather_after(set, history_set, args, true, (cudaStream_t)stream);
 }
 
 int jn_env_rewards(const int64_t* positions, const uint32_t* visited, const uint32_t* bbox, const uint8_t* has_stopped,
@@ -671,7 +914,7 @@ int jn_env_rewards(const int64_t* positions, const uint32_t* visited, const uint
   if (int rc = current_device_info(dev)) return rc;
   jnk::env_rewards_kernel<<<grid_for(n, 128, dev.sm_count * 16), 128, 0, (cudaStream_t)stream>>>(
       positions, visited, bbox, has_stopped, n, rows, cols, jn_bitmap_words(rows, cols), cost, stop_enabled, rewards);
-  JN_CUDA(cudaGetLastError());
+  JN_LAUNCHED();
   return JN_OK;
 }
 
@@ -685,7 +928,7 @@ int jn_env_props(const uint32_t* visited, const uint32_t* bbox, const uint8_t* h
   const int wpb = 4;
   jnk::env_props_kernel<<<grid_for(n, wpb, dev.sm_count * 16), wpb * 32, 0, (cudaStream_t)stream>>>(
       visited, bbox, has_stopped, n, jn_bitmap_words(rows, cols), stop_enabled, prop_patches, terminated);
-  JN_CUDA(cudaGetLastError());
+  JN_LAUNCHED();
   return JN_OK;
 }
 
@@ -700,7 +943,7 @@ int jn_returns(const float* rewards_tn, const uint8_t* terminated_tn, int T, int
              "jn_returns: NULL pointer");
   jnk::returns_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards_tn, terminated_tn, T, n, rewards_out,
                                                                          masks, logit_masks, returns);
-  JN_CUDA(cudaGetLastError());
+  JN_LAUNCHED();
   return JN_OK;
 }
 
@@ -711,7 +954,7 @@ int jn_returns_rows(const float* rewards, int64_t rewards_row_stride, const uint
   JN_REQUIRE(rewards && logit_masks && returns, "jn_returns_rows: NULL pointer");
   jnk::returns_rows_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards, rewards_row_stride, logit_masks,
                                                                               masks_row_stride, T, n, returns);
-  JN_CUDA(cudaGetLastError());
+  JN_LAUNCHED();
   return JN_OK;
 }
 
@@ -726,7 +969,7 @@ int jn_tile_lookup(const int64_t* traj_positions, const int32_t* traj_src, int T
   if (int rc = current_device_info(dev)) return rc;
   jnk::tile_lookup_kernel<<<grid_for(n_queries, 128, dev.sm_count * 8), 128, 0, (cudaStream_t)stream>>>(
       traj_positions, traj_src, T, query_positions, query_src, n_queries, slab_base, out_positions, out_src);
-  JN_CUDA(cudaGetLastError());
+  JN_LAUNCHED();
   return JN_OK;
 }
 
@@ -740,7 +983,7 @@ int jn_visit_sources(const int64_t* positions, int32_t* first_slot, int n, int r
   if (int rc = current_device_info(dev)) return rc;
   jnk::visit_sources_kernel<<<grid_for(n, 128, dev.sm_count * 8), 128, 0, (cudaStream_t)stream>>>(
       positions, first_slot, n, rows, cols, slots, t, host_src, history_src, status);
-  JN_CUDA(cudaGetLastError());
+  JN_LAUNCHED();
   return JN_OK;
 }
 
@@ -753,7 +996,7 @@ int jn_tile_dedupe(const int64_t* traj_positions, const int32_t* traj_src, int n
   if (int rc = current_device_info(dev)) return rc;
   jnk::tile_dedupe_kernel<<<grid_for(n_slots, 128, dev.sm_count * 8), 128, 0, (cudaStream_t)stream>>>(
       traj_positions, traj_src, n_slots, T, first_src, repeat_src);
-  JN_CUDA(cudaGetLastError());
+  JN_LAUNCHED();
   return JN_OK;
 }
 
@@ -774,7 +1017,7 @@ int jn_traj_expand(const int32_t* start_yx, const int32_t* seg_begin, const int3
                                                    draws, area_bitmaps, words_per_item, cols, n, T, positions,
                                                    current_actions, next_actions, labels, masks, gather_src, ep_len,
                                                    status);
-  JN_CUDA(cudaGetLastError());
+  JN_LAUNCHED();
   return JN_OK;
 }
 

@@ -156,6 +156,14 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// ---- programmatic dependent launch (sm_90+) ---------------------------------------------------
+// A kernel that executes pdl_launch_dependents() lets the next kernel of the stream -- when that one was
+// launched with the programmatic-serialization attribute -- start before this one has finished; pdl_wait() in
+// the dependent kernel blocks until the prerequisite grid has completed and its writes are visible (a no-op
+// for a normally launched kernel).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // streaming stores (the crops are consumed by the next kernel, never re-read by us)
 __device__ __forceinline__ void st_f4(float* p, float a, float b, float c, float d) {
   asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");

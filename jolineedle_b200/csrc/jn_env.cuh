@@ -27,7 +27,12 @@ __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(kFullM
 // few bitmap words a box can touch, lane = bit evaluates its patch and a ballot assembles the word, which
 // lane (word % 32) ORs into its accumulator -- so a 5x6 grid keeps 30 lanes busy instead of one, and a
 // 32x32 grid only visits the one or two words under each box.
-__global__ void patch_bitmaps_kernel(const int64_t* __restrict__ bboxes, const int32_t* __restrict__ n_boxes, int n,
+//
+// Box coordinates are int64 pixels, or float64 (kFloat: rule 1 only) for boxes that are not whole pixels -- the
+// dataset's minimum-size resize (dataset.py:258-270) scales them -- with the reference's python float arithmetic
+// restated in IEEE doubles: floor(v / P) patch ranges, `oh * ow / P**2 > 0.05`, centre floor((a + b) / 2).
+template <bool kFloat>
+__global__ void patch_bitmaps_kernel(const void* __restrict__ bboxes_, const int32_t* __restrict__ n_boxes, int n,
                                      int max_boxes, int P, int grid_rows, int grid_cols,
                                      const int32_t* __restrict__ rows_arr, const int32_t* __restrict__ cols_arr,
                                      int rule, uint32_t* __restrict__ out, int words_per_item) {
@@ -42,11 +47,25 @@ __global__ void patch_bitmaps_kernel(const int64_t* __restrict__ bboxes, const i
     for (int wb = 0; wb < words_per_item; wb += 32) {  // blocks of 32 words: lane l accumulates word wb + l
       uint32_t acc = 0;
       for (int k = 0; k < nb; ++k) {
-        const int64_t* b = bboxes + ((long long)e * max_boxes + k) * 4;
-        const long long x1 = b[0], y1 = b[1], x2 = b[2], y2 = b[3];
+        const long long box_at = ((long long)e * max_boxes + k) * 4;
+        long long x1 = 0, y1 = 0, x2 = 0, y2 = 0;
+        double fx1 = 0, fy1 = 0, fx2 = 0, fy2 = 0;
+        if (kFloat) {
+          const double* b = static_cast<const double*>(bboxes_) + box_at;
+          fx1 = b[0]; fy1 = b[1]; fx2 = b[2]; fy2 = b[3];
+        } else {
+          const int64_t* b = static_cast<const int64_t*>(bboxes_) + box_at;
+          x1 = b[0]; y1 = b[1]; x2 = b[2]; y2 = b[3];
+        }
         long long px_lo, px_hi, py_lo, py_hi;  // inclusive candidate patch range
         long long cpx = -1, cpy = -1;          // centre patch (rule 1)
-        if (rule == 0) {
+        if (kFloat) {
+          const double dp = (double)P;
+          px_lo = (long long)floor(__ddiv_rn(fx1, dp)); px_hi = (long long)floor(__ddiv_rn(fx2, dp));
+          py_lo = (long long)floor(__ddiv_rn(fy1, dp)); py_hi = (long long)floor(__ddiv_rn(fy2, dp));
+          cpx = (long long)floor(__ddiv_rn(floor(__ddiv_rn(__dadd_rn(fx1, fx2), 2.0)), dp));
+          cpy = (long long)floor(__ddiv_rn(floor(__ddiv_rn(__dadd_rn(fy1, fy2), 2.0)), dp));
+        } else if (rule == 0) {
           const long long x1c = lmin(lmax(x1, 0), W), x2c = lmin(lmax(x2 + 1, 0), W);
           const long long y1c = lmin(lmax(y1, 0), H), y2c = lmin(lmax(y2 + 1, 0), H);
           if (x1c >= x2c || y1c >= y2c) continue;
@@ -75,9 +94,15 @@ __global__ void patch_bitmaps_kernel(const int64_t* __restrict__ bboxes, const i
             } else {
               hit = (x == cpx && y == cpy);
               if (!hit && x >= px_lo && x <= px_hi && y >= py_lo && y <= py_hi) {
-                const long long oh = lmin((long long)(y + 1) * P, y2) - lmax((long long)y * P, y1);
-                const long long ow = lmin((long long)(x + 1) * P, x2) - lmax((long long)x * P, x1);
-                hit = 20 * (oh * ow) > (long long)P * P;
+                if (kFloat) {
+                  const double oh = __dsub_rn(fmin((double)((long long)(y + 1) * P), fy2), fmax((double)((long long)y * P), fy1));
+                  const double ow = __dsub_rn(fmin((double)((long long)(x + 1) * P), fx2), fmax((double)((long long)x * P), fx1));
+                  hit = __ddiv_rn(__dmul_rn(oh, ow), (double)((long long)P * P)) > 0.05;
+                } else {
+                  const long long oh = lmin((long long)(y + 1) * P, y2) - lmax((long long)y * P, y1);
+                  const long long ow = lmin((long long)(x + 1) * P, x2) - lmax((long long)x * P, x1);
+                  hit = 20 * (oh * ow) > (long long)P * P;
+                }
               }
             }
           }
@@ -138,8 +163,10 @@ __global__ void split_boxes_kernel(const int64_t* __restrict__ bboxes, int n, in
   }
 }
 
-// local_bboxes (simple_env.py:231-268): one thread per (item, box).
-__global__ void local_boxes_kernel(const int64_t* __restrict__ bboxes, const int32_t* __restrict__ n_boxes,
+// local_bboxes (simple_env.py:231-268): one thread per (item, box).  kFloat: float64 boxes, differences taken in
+// double and rounded to float32 once, as python floats going into a FloatTensor are.
+template <bool kFloat>
+__global__ void local_boxes_kernel(const void* __restrict__ bboxes_, const int32_t* __restrict__ n_boxes,
                                    int max_boxes, int P, const int64_t* __restrict__ positions,
                                    const int32_t* __restrict__ src_index, int n_items, float* __restrict__ out) {
   const long long total = (long long)n_items * max_boxes;
@@ -150,13 +177,24 @@ __global__ void local_boxes_kernel(const int64_t* __restrict__ bboxes, const int
     float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f;
     const int e = src_index ? src_index[item] : item;
     if (e >= 0 && k < (n_boxes ? n_boxes[e] : max_boxes)) {
-      const int64_t* b = bboxes + ((long long)e * max_boxes + k) * 4;
+      const long long box_at = ((long long)e * max_boxes + k) * 4;
       const long long px1 = positions[2 * (long long)item + 1] * P, py1 = positions[2 * (long long)item] * P;
       const long long px2 = px1 + P, py2 = py1 + P;
-      const long long x1 = lmax(px1, b[0]), y1 = lmax(py1, b[1]);
-      const long long x2 = lmin(px2, b[2]), y2 = lmin(py2, b[3]);
-      if (x1 < x2 && y1 < y2) {  // the px1 <= x1 and x2 <= px2 halves hold by construction
-        v1 = (float)(x1 - px1); v2 = (float)(y1 - py1); v3 = (float)(x2 - px1); v4 = (float)(y2 - py1); v5 = 1.f;
+      if (kFloat) {
+        const double* b = static_cast<const double*>(bboxes_) + box_at;
+        const double x1 = fmax((double)px1, b[0]), y1 = fmax((double)py1, b[1]);
+        const double x2 = fmin((double)px2, b[2]), y2 = fmin((double)py2, b[3]);
+        if (x1 < x2 && y1 < y2) {
+          v1 = (float)__dsub_rn(x1, (double)px1); v2 = (float)__dsub_rn(y1, (double)py1);
+          v3 = (float)__dsub_rn(x2, (double)px1); v4 = (float)__dsub_rn(y2, (double)py1); v5 = 1.f;
+        }
+      } else {
+        const int64_t* b = static_cast<const int64_t*>(bboxes_) + box_at;
+        const long long x1 = lmax(px1, b[0]), y1 = lmax(py1, b[1]);
+        const long long x2 = lmin(px2, b[2]), y2 = lmin(py2, b[3]);
+        if (x1 < x2 && y1 < y2) {  // the px1 <= x1 and x2 <= px2 halves hold by construction
+          v1 = (float)(x1 - px1); v2 = (float)(y1 - py1); v3 = (float)(x2 - px1); v4 = (float)(y2 - py1); v5 = 1.f;
+        }
       }
     }
     o[0] = v0; o[1] = v1; o[2] = v2; o[3] = v3; o[4] = v4; o[5] = v5;
@@ -164,139 +202,179 @@ __global__ void local_boxes_kernel(const int64_t* __restrict__ bboxes, const int
 }
 
 // ------------------------------------------------------------------------------------------
-// K2: reset / step / props -- one warp per episode
+// K2: reset / step / props
 // ------------------------------------------------------------------------------------------
-__global__ void env_reset_kernel(const int64_t* __restrict__ positions, uint32_t* __restrict__ visited,
-                                 int64_t* __restrict__ steps, uint8_t* __restrict__ has_stopped, int n, int rows,
-                                 int cols, int words, int32_t* __restrict__ status) {
-  const int warps_per_block = blockDim.x >> 5;
-  const int lane = threadIdx.x & 31;
-  for (int e = blockIdx.x * warps_per_block + (threadIdx.x >> 5); e < n; e += gridDim.x * warps_per_block) {
-    const long long y = positions[2 * (long long)e], x = positions[2 * (long long)e + 1];
-    const bool ok = (y >= 0 && y < rows && x >= 0 && x < cols);
-    const int bit = ok ? (int)(y * cols + x) : -1;
-    for (int w = lane; w < words; w += 32)
-      visited[(long long)e * words + w] = (bit >= 0 && (bit >> 5) == w) ? (1u << (bit & 31)) : 0u;
-    if (lane == 0) {
-      steps[e] = 0;
-      has_stopped[e] = 0;
-      if (!ok && status) atomicOr(status, 1);
-    }
-  }
-}
+// Per-step argument block of the env kernels (borrowed device pointers; see jn_env_step / jn_env_step_gather).
+struct StepArgs {
+  const int64_t* pos_in;   // [n, 2] positions before the move
+  const int64_t* actions;  // [n]
+  int64_t* pos_out;        // [n, 2] positions after the move (may alias pos_in)
+  uint32_t* visited;       // [n, words]
+  const uint32_t* bbox;    // [n, words]
+  int64_t* steps;          // [n]
+  uint8_t* has_stopped;    // [n]
+  float* rewards;          // [n]
+  uint8_t* terminated;     // [n]
+  uint8_t* truncated;      // [n]
+  // first-visit table of the zero-copy env (all null when unused): see visit_sources_kernel
+  int32_t* first_slot;     // [n, rows*cols]
+  int32_t* host_src;       // [n]
+  int32_t* history_src;    // [n]
+  unsigned long long* host_tiles;  // running count of first visits (= tiles read from the host), or null
+  int32_t* status;
+  int n, rows, cols, words, max_ep_len, stop_enabled, slots, t;
+  float cost;
+};
 
-// A group of G lanes (G = the power of two >= the number of bitmap words, at most 32) owns an episode:
-// lane k of the group owns words k, k+G, ...; a warp steps 32/G episodes at once (32x32 grid: 32 words, one
-// warp per episode; 8x8 grid: 2 words, 16 episodes per warp).  Counts are reduced inside the group with
-// xor-shuffles.  Every lane of a group computes the scalar tail (same values, uniform instructions) and lane 0
-// of the group stores, so that no instruction runs with a single active lane.
-template <int G>
-__global__ void env_step_group_kernel(const int64_t* __restrict__ pos_in, const int64_t* __restrict__ actions,
-                                      int64_t* __restrict__ pos_out, uint32_t* __restrict__ visited,
-                                      const uint32_t* __restrict__ bbox, int64_t* __restrict__ steps,
-                                      uint8_t* __restrict__ has_stopped, float* __restrict__ rewards,
-                                      uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, int n,
-                                      int rows, int cols, int words, int max_ep_len, float cost, int stop_enabled,
-                                      int32_t* __restrict__ status) {
-  constexpr int kPerWarp = 32 / G;
-  const int warps_per_block = blockDim.x >> 5;
-  const int lane = threadIdx.x & 31, sub = lane & (G - 1), group = lane / G;
-  const int stride = gridDim.x * warps_per_block * kPerWarp;
-  for (int base = (blockIdx.x * warps_per_block + (threadIdx.x >> 5)) * kPerWarp; base < n; base += stride) {
-    const int e = base + group;
-    const bool live = e < n;  // lanes past the end still take part in the shuffles
-    // --- move + clamp, sticky stop (general_env.py:209-233)
-    const long long a_raw = live ? actions[e] : (long long)kStop;
-    const bool bad_action = a_raw < 0 || a_raw > kStop;
-    if (bad_action && sub == 0 && status) atomicOr(status, 2);
-    const long long a = bad_action ? (long long)kStop : a_raw;  // invalid code: no move (flagged); the reference raises
-    long long y = (live ? pos_in[2 * (long long)e] : 0) + kActionDy[a];
-    long long x = (live ? pos_in[2 * (long long)e + 1] : 0) + kActionDx[a];
-    y = lmin(lmax(y, 0), rows - 1);
-    x = lmin(lmax(x, 0), cols - 1);
-    const bool stopped = live && ((has_stopped[e] != 0) || a_raw == kStop);
-    const int bit = (int)(y * cols + x);
-    // --- bitmaps
-    int found = 0, every = 0, missing_after = 0, fresh = 0;
-    if (live) {
-      for (int w = sub; w < words; w += G) {
-        const uint32_t v = visited[(long long)e * words + w];
-        const uint32_t b = bbox[(long long)e * words + w];
-        found += __popc(v & b);  // counts use the map BEFORE marking (general_env.py:347)
-        every += __popc(b);
-        uint32_t v_new = v;
-        if ((bit >> 5) == w) {
-          const uint32_t m = 1u << (bit & 31);
-          fresh = ((b & m) != 0 && (v & m) == 0) ? 1 : 0;
-          v_new = v | m;
-          visited[(long long)e * words + w] = v_new;
-        }
-        missing_after += __popc(b & ~v_new);
+// Clears the episode state and marks the start patch (init_env_variables + the tail of reset,
+// general_env.py:117-142,164).  One thread per bitmap word; with a first-visit table, one thread per patch of
+// the table as well (entry = slot 0 for the start patch, -1 elsewhere) and the sources of slot 0.
+__global__ void env_reset_kernel(const StepArgs a) {
+  pdl_launch_dependents();
+  const long long cells = a.first_slot ? (long long)a.rows * a.cols : 0;
+  const long long per = a.words > cells ? a.words : cells;
+  const long long total = (long long)a.n * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i / per), k = (int)(i - (long long)e * per);
+    const long long y = a.pos_out[2 * (long long)e], x = a.pos_out[2 * (long long)e + 1];
+    const bool ok = (y >= 0 && y < a.rows && x >= 0 && x < a.cols);
+    const int bit = ok ? (int)(y * a.cols + x) : -1;
+    if (k < a.words) a.visited[(long long)e * a.words + k] = (bit >= 0 && (bit >> 5) == k) ? (1u << (bit & 31)) : 0u;
+    if (k < cells) a.first_slot[(long long)e * cells + k] = (k == bit) ? 0 : -1;
+    if (k == 0) {
+      a.steps[e] = 0;
+      a.has_stopped[e] = 0;
+      if (!ok && a.status) atomicOr(a.status, 1);
+      if (a.first_slot) {
+        a.host_src[e] = ok ? e : -2; a.history_src[e] = -2;
+        if (ok && a.host_tiles) atomicAdd(a.host_tiles, 1ull);
       }
     }
-#pragma unroll
-    for (int off = G / 2; off > 0; off >>= 1) {
-      found += __shfl_xor_sync(kFullMask, found, off);
-      every += __shfl_xor_sync(kFullMask, every, off);
-      missing_after += __shfl_xor_sync(kFullMask, missing_after, off);
-      fresh |= __shfl_xor_sync(kFullMask, fresh, off);
-    }
-    // --- reward = fl32(fl32(fresh + cost) + stop_eval), general_env.py:334-358
-    float r = __fadd_rn(fresh ? 1.0f : 0.0f, cost);
-    if (stop_enabled) {
-      const int stop_eval = stopped ? (found == every ? found : found - every) : 0;
-      r = __fadd_rn(r, (float)stop_eval);
-    }
-    const long long s = (live ? steps[e] : 0) + 1;
-    if (live && sub == 0) {
-      rewards[e] = r;
-      steps[e] = s;
-      has_stopped[e] = stopped ? 1 : 0;
-      truncated[e] = s >= max_ep_len ? 1 : 0;
-      terminated[e] = stop_enabled ? (stopped ? 1 : 0) : (missing_after == 0 ? 1 : 0);
-      pos_out[2 * (long long)e] = y;
-      pos_out[2 * (long long)e + 1] = x;
-    }
   }
 }
 
-// Single-word grids (rows*cols <= 32, e.g. the 5x6 LARD grid of cfg 2/3): the whole bitmap of an
-// episode is one register, so a *lane* owns an episode and a warp steps 32 of them with every lane
-// busy with 16-byte position loads and stores.  Same arithmetic, same order of operations as the group
-// kernel above (whose G = 1 instance serves one-word grids with unaligned position buffers).
-__global__ void env_step_lane_kernel(const int64_t* __restrict__ pos_in, const int64_t* __restrict__ actions,
-                                     int64_t* __restrict__ pos_out, uint32_t* __restrict__ visited,
-                                     const uint32_t* __restrict__ bbox, int64_t* __restrict__ steps,
-                                     uint8_t* __restrict__ has_stopped, float* __restrict__ rewards,
-                                     uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, int n, int rows,
-                                     int cols, int max_ep_len, float cost, int stop_enabled,
-                                     int32_t* __restrict__ status) {
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    long long a = actions[e];
-    const bool valid = (a >= 0 && a <= kStop);
-    if (!valid) {
-      if (status) atomicOr(status, 2);
-      a = kStop;
+// One env step (general_env.py:172-207).  A warp owns 32 consecutive episodes and every instruction of the
+// kernel runs with all of its lanes on useful work:
+//
+//   phase A  lane = episode: action, position (coalesced loads), move + clamp, sticky stop flag, bit index;
+//   phase B  lanes = bitmap words: G lanes (G = the power of two >= the number of words, at most 32) read the
+//            visited / bbox words of one episode, 32/G episodes at a time; popc counts are packed two to a
+//            register and reduced inside the group (one REDUX per register when the group is the warp),
+//            then handed to the lane that owns the episode.  Loads only -- the visited bit is set in phase C
+//            with a RED.OR, so that the unrolled loop keeps every load of the warp in flight at once;
+//   phase C  lane = episode: reward = fl32(fl32(fresh + cost) + stop_eval), flags, counters; coalesced stores.
+//
+// One-word grids (5x6 LARD grid, G = 1) degenerate to a lane per episode; the 32x32 aerial grid (G = 32) to 32
+// warp-wide iterations.  Counts are 16-bit fields: grids of up to 65535 patches.
+template <int G>
+__global__ void __launch_bounds__(64) env_step_kernel(const __grid_constant__ StepArgs a) {
+  pdl_launch_dependents();  // the gather that follows derives its positions from pos_in + actions itself
+  constexpr int kPer = 32 / G;
+  const int lane = threadIdx.x & 31, sub = lane & (G - 1), grp = lane / G;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const bool vec = ((reinterpret_cast<uintptr_t>(a.pos_in) | reinterpret_cast<uintptr_t>(a.pos_out)) & 15) == 0;
+  for (int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < a.n; base += n_warps * 32) {
+    // ---- phase A
+    const int e = base + lane;
+    const bool live = e < a.n;
+    long long act = live ? a.actions[e] : (long long)kStop;
+    const bool bad = act < 0 || act > kStop;  // invalid code: flagged, no move (the reference raises)
+    if (bad) {
+      if (a.status) atomicOr(a.status, 2);
+      act = kStop;
     }
-    const longlong2 p = reinterpret_cast<const longlong2*>(pos_in)[e];  // (y, x), 16-byte aligned rows
-    const long long y = lmin(lmax(p.x + kActionDy[a], 0), rows - 1);
-    const long long x = lmin(lmax(p.y + kActionDx[a], 0), cols - 1);
-    const bool stopped = (has_stopped[e] != 0) || (valid && a == kStop);
-    const uint32_t m = 1u << (int)(y * cols + x);
-    const uint32_t v = visited[e], b = bbox[e];
-    const int found = __popc(v & b), every = __popc(b);  // from the map BEFORE marking
-    const bool fresh = (b & m) != 0 && (v & m) == 0;
-    const uint32_t v_new = v | m;
-    visited[e] = v_new;
-    float r = __fadd_rn(fresh ? 1.0f : 0.0f, cost);
-    if (stop_enabled) r = __fadd_rn(r, (float)(stopped ? (found == every ? found : found - every) : 0));
-    rewards[e] = r;
-    const long long s = steps[e] + 1;
-    steps[e] = s;
-    has_stopped[e] = stopped ? 1 : 0;
-    truncated[e] = s >= max_ep_len ? 1 : 0;
-    terminated[e] = stop_enabled ? (stopped ? 1 : 0) : ((b & ~v_new) == 0 ? 1 : 0);
-    reinterpret_cast<longlong2*>(pos_out)[e] = make_longlong2(y, x);
+    long long y = 0, x = 0;
+    if (live) {
+      if (vec) {
+        const longlong2 p = reinterpret_cast<const longlong2*>(a.pos_in)[e];
+        y = p.x; x = p.y;
+      } else {
+        y = a.pos_in[2 * (long long)e]; x = a.pos_in[2 * (long long)e + 1];
+      }
+    }
+    y = lmin(lmax(y + kActionDy[act], 0), a.rows - 1);  // general_env.py:214-231
+    x = lmin(lmax(x + kActionDx[act], 0), a.cols - 1);
+    const bool stopped = live && (a.has_stopped[e] != 0 || (!bad && act == kStop));  // sticky, :233
+    const int bit = (int)(y * a.cols + x);
+    // ---- phase B
+    // all loads first (independent: 2 * G in flight per lane), then the arithmetic
+    uint32_t vv[G], bb[G];
+#pragma unroll
+    for (int it = 0; it < G; ++it) {
+      const int ej = base + it * kPer + grp;
+      const bool ok = ej < a.n && sub < a.words;
+      const long long idx = (long long)ej * a.words + sub;
+      vv[it] = ok ? a.visited[idx] : 0u;
+      bb[it] = ok ? a.bbox[idx] : 0u;
+    }
+    uint32_t mine_fe = 0, mine_mf = 0;  // found | every << 16;  fresh | missing_after << 1
+#pragma unroll
+    for (int it = 0; it < G; ++it) {
+      const int j = it * kPer + grp;  // episode of this group, relative to base
+      const int bit_j = __shfl_sync(kFullMask, bit, j);
+      const uint32_t v = vv[it], b = bb[it];
+      const uint32_t m = (bit_j >> 5) == sub ? (1u << (bit_j & 31)) : 0u;
+      uint32_t fe = __popc(v & b) | (__popc(b) << 16);  // counts use the map BEFORE marking (general_env.py:347)
+      uint32_t mf = ((b & m & ~v) ? 1u : 0u) | (__popc(b & ~(v | m)) << 1);
+      if (G == 32 && a.words > 32 && base + j < a.n) {  // grids of more than 1024 patches: the remaining words
+        const long long row = (long long)(base + j) * a.words;
+#pragma unroll 1
+        for (int w = sub + 32; w < a.words; w += 32) {
+          const uint32_t v2 = a.visited[row + w], b2 = a.bbox[row + w];
+          const uint32_t m2 = (bit_j >> 5) == w ? (1u << (bit_j & 31)) : 0u;
+          fe += __popc(v2 & b2) | (__popc(b2) << 16);
+          mf += ((b2 & m2 & ~v2) ? 1u : 0u) | (__popc(b2 & ~(v2 | m2)) << 1);
+        }
+      }
+      if (G == 32) {
+        fe = __reduce_add_sync(kFullMask, fe);
+        mf = __reduce_add_sync(kFullMask, mf);
+        if (lane == it) { mine_fe = fe; mine_mf = mf; }
+      } else {
+#pragma unroll
+        for (int off = G / 2; off > 0; off >>= 1) {
+          fe += __shfl_xor_sync(kFullMask, fe, off);
+          mf += __shfl_xor_sync(kFullMask, mf, off);
+        }
+        // lane L owns episode L: handled in iteration L / kPer by group L % kPer
+        const uint32_t got_fe = __shfl_sync(kFullMask, fe, (lane % kPer) * G);
+        const uint32_t got_mf = __shfl_sync(kFullMask, mf, (lane % kPer) * G);
+        if (lane / kPer == it) { mine_fe = got_fe; mine_mf = got_mf; }
+      }
+    }
+    // ---- phase C
+    bool first_visit = false;
+    if (live) {
+      const int found = (int)(mine_fe & 0xFFFFu), every = (int)(mine_fe >> 16);
+      const bool fresh = (mine_mf & 1u) != 0, done = (mine_mf >> 1) == 0;
+      float r = __fadd_rn(fresh ? 1.0f : 0.0f, a.cost);  // general_env.py:334-358
+      if (a.stop_enabled) r = __fadd_rn(r, (float)(stopped ? (found == every ? found : found - every) : 0));
+      const long long s = a.steps[e] + 1;
+      atomicOr(a.visited + (long long)e * a.words + (bit >> 5), 1u << (bit & 31));
+      a.rewards[e] = r;
+      a.steps[e] = s;
+      a.has_stopped[e] = stopped ? 1 : 0;
+      a.truncated[e] = s >= a.max_ep_len ? 1 : 0;
+      a.terminated[e] = a.stop_enabled ? (stopped ? 1 : 0) : (done ? 1 : 0);
+      if (vec) {
+        reinterpret_cast<longlong2*>(a.pos_out)[e] = make_longlong2(y, x);
+      } else {
+        a.pos_out[2 * (long long)e] = y; a.pos_out[2 * (long long)e + 1] = x;
+      }
+      if (a.first_slot) {  // zero-copy env: first visit -> read the tile from the host, else from the history
+        int32_t* cell = a.first_slot + (long long)e * a.rows * a.cols + bit;
+        const int seen = *cell;
+        first_visit = seen < 0;
+        if (first_visit) *cell = a.t;
+        a.host_src[e] = first_visit ? e : -2;
+        a.history_src[e] = first_visit ? -2 : e * a.slots + seen;
+      }
+    }
+    if (a.host_tiles) {
+      const unsigned firsts = __ballot_sync(kFullMask, first_visit);
+      if (lane == 0 && firsts) atomicAdd(a.host_tiles, (unsigned long long)__popc(firsts));
+    }
   }
 }
 

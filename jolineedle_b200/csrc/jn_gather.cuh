@@ -34,7 +34,7 @@ struct ImageRec {        // one per image when the set has several slabs (<= 32 
 struct GatherArgs {
   const uint8_t* base;        // single-slab sets: first byte of image 0
   const ImageRec* images;     // multi-slab sets: per-image records (device memory), else null
-  const int64_t* positions;   // [n_items, 2] (y, x) patch coordinates
+  const int64_t* positions;   // [n_items, 2] (y, x) patch coordinates; null = patch (0, 0) for every item
   const int32_t* src_index;   // [n_items] image per item (negative = zero fill) or null = identity
   const int32_t* shifts;      // [n_images, 2] (ty, tx) integer translation of each image (zero fill) or null
   uint8_t* out;
@@ -53,6 +53,12 @@ struct GatherArgs {
   int* work_counter;            // xform kernel: {next unclaimed chunk, CTAs done}; zero before and after a launch
   int padded;                   // image sizes are rounded up to the patch grid, pixels outside the image are zeros
   int skip_negative;            // negative src_index: 1 = leave the output tile untouched, 0 = zero-fill it
+  // fused env step (jn_env_step_gather): `positions` are the positions BEFORE the move and the kernel applies
+  // actions[item] itself (move + clamp to grid_rows x grid_cols, general_env.py:209-231), so that it does not
+  // depend on the step kernel it was launched behind
+  const int64_t* actions;
+  int grid_rows, grid_cols;
+  int wait_prior;               // 1 = griddepcontrol.wait before the first index load (src_index comes from the step kernel)
 };
 
 struct Chunk {
@@ -68,6 +74,20 @@ __device__ __forceinline__ int grid_extent(const GatherArgs& a, int size) {
   return a.padded ? (size + a.patch - 1) / a.patch * a.patch : size;
 }
 
+// Patch coordinates of item `item`: positions[item], moved by actions[item] when the gather runs fused with
+// an env step (same arithmetic as env_step_kernel: invalid action codes do not move).
+__device__ __forceinline__ void item_position(const GatherArgs& a, long long item, long long& y, long long& x) {
+  if (!a.positions) { y = 0; x = 0; return; }  // sets of one-patch images
+  y = a.positions[2 * item];
+  x = a.positions[2 * item + 1];
+  if (a.actions) {
+    long long act = a.actions[item];
+    if (act < 0 || act > kStop) act = kStop;
+    y = lmin(lmax(y + kActionDy[act], 0), a.grid_rows - 1);
+    x = lmin(lmax(x + kActionDx[act], 0), a.grid_cols - 1);
+  }
+}
+
 // Decode chunk q.  Out-of-grid positions are reported once and treated as "skip" (src = null,
 // skip = true); negative src_index means zero fill (src = null, skip = false).
 __device__ __forceinline__ bool decode_chunk(const GatherArgs& a, int q, Chunk& c) {
@@ -80,18 +100,20 @@ __device__ __forceinline__ bool decode_chunk(const GatherArgs& a, int q, Chunk& 
   c.plane = 0;
   const int img = a.src_index ? a.src_index[c.item] : c.item;
   if (img < 0) return a.skip_negative != 0 || img < -1;  // -1: zero fill (or skip on request); <= -2: always skip
-  const long long y = a.positions[2 * (long long)c.item], x = a.positions[2 * (long long)c.item + 1];
+  long long y, x;
+  item_position(a, c.item, y, x);
   const uint8_t* base;
   int h, w;
   if (a.images) {
-    const ImageRec r = a.images[img];
+    const ImageRec r = a.images[img < a.n_images ? img : 0];  // (a bad index is reported below, never dereferenced)
     base = r.base; h = r.height; w = r.width;
     c.plane = r.plane0 + c.channel;
   } else {
     base = a.base + (long long)img * a.image_stride; h = a.height; w = a.width;
     c.plane = img * a.channels + c.channel;
   }
-  if (img >= a.n_images || y < 0 || x < 0 || (y + 1) * a.patch > h || (x + 1) * a.patch > w) {
+  if (img >= a.n_images || y < 0 || x < 0 || (y + 1) * a.patch > grid_extent(a, h) ||
+      (x + 1) * a.patch > grid_extent(a, w)) {
     if (a.status && c.channel == 0 && c.row0 == 0) atomicOr(a.status, 1);
     return true;  // skip
   }
@@ -127,6 +149,7 @@ gather_copy_kernel(const __grid_constant__ GatherArgs a, const __grid_constant__
   for (int i = lane * 16; i < kZeroBytes; i += 32 * 16) *reinterpret_cast<uint4*>(zero + i) = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();  // zeros (generic proxy) -> visible to the bulk stores (async proxy)
   __syncwarp();
+  if (a.wait_prior) pdl_wait();  // everything above overlapped the tail of the kernel before us
 
   const int grid = gridDim.x;
   const int mine = a.total_chunks > (int)blockIdx.x ? (a.total_chunks - (int)blockIdx.x + grid - 1) / grid : 0;
@@ -365,7 +388,8 @@ __device__ __forceinline__ ChunkPlan plan_chunk(const GatherArgs& a, int q, bool
     p.flags = (a.skip_negative || img < -1) ? kDescSkip : kDescZero;
     return p;
   }
-  const long long y = a.positions[2 * (long long)item], x = a.positions[2 * (long long)item + 1];
+  long long y, x;
+  item_position(a, item, y, x);
   const uint8_t* base;
   int h, w;
   if (a.images) {
@@ -424,6 +448,7 @@ gather_xform_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
     if (tensor) prefetch_tensormap(&map0);
   }
   __syncthreads();
+  if (a.wait_prior) pdl_wait();  // barrier init / tensor-map prefetch overlapped the tail of the kernel before us
 
   int st = 0;
   uint32_t phase = 0;  // parity of the ring round this warp is in
@@ -533,6 +558,7 @@ gather_xform_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
 // outside the translated image are zeros.  Needs P % 4 == 0 and a 16-byte aligned output.
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const GatherArgs a, const int out_f32, const int normalize, const int focus) {
+  if (a.wait_prior) pdl_wait();
   const int P = a.patch, lane = threadIdx.x & 31;
   const long long units = (long long)a.n_items * a.channels * P;  // (item, channel, row)
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -548,9 +574,9 @@ gather_rows_kernel(const GatherArgs a, const int out_f32, const int normalize, c
     bool zero_row = img < 0;
     if (zero_row && (a.skip_negative || img < -1)) continue;
     if (!zero_row) {
-      y = a.positions[2 * (long long)item]; x = a.positions[2 * (long long)item + 1];
+      item_position(a, item, y, x);
       if (a.images) {
-        const ImageRec rec = a.images[img];
+        const ImageRec rec = a.images[img < a.n_images ? img : 0];
         base = rec.base; h = rec.height; w = rec.width;
       } else {
         base = a.base + (long long)img * a.image_stride; h = a.height; w = a.width;
@@ -603,6 +629,7 @@ gather_rows_kernel(const GatherArgs a, const int out_f32, const int normalize, c
 // ------------------------------------------------------------------------------------------
 // One thread per output element of the plain layout; handles every dtype / flag combination.
 __global__ void gather_ldg_kernel(const GatherArgs a, const int out_f32, const int normalize, const int focus) {
+  if (a.wait_prior) pdl_wait();
   const int P = a.patch;
   const long long per_item = (long long)a.channels * P * P;
   const long long total = per_item * a.n_items;
@@ -618,11 +645,12 @@ __global__ void gather_ldg_kernel(const GatherArgs a, const int out_f32, const i
     uint8_t bv = 0;
     if (img < 0 && (a.skip_negative || img < -1)) continue;
     if (img >= 0) {
-      const long long y = a.positions[2 * (long long)item], x = a.positions[2 * (long long)item + 1];
+      long long y, x;
+      item_position(a, item, y, x);
       const uint8_t* base;
       int h, w;
       if (a.images) {
-        const ImageRec rec = a.images[img];
+        const ImageRec rec = a.images[img < a.n_images ? img : 0];
         base = rec.base; h = rec.height; w = rec.width;
       } else {
         base = a.base + (long long)img * a.image_stride; h = a.height; w = a.width;

@@ -117,8 +117,12 @@ __global__ void tile_dedupe_kernel(const int64_t* __restrict__ traj_pos, const i
 //            its position is closed form, start + sign(d) * min(j, |d|) per axis.
 //   phase 3  tail truncation: with ep_len > T only records [ep_len - T, ep_len) are kept.
 //
-// Segment tables live in shared memory (kMaxSeg per warp); episodes with more segments than
-// that raise status bit 8 and are left masked out.
+// Segment tables live in shared memory, kMaxSeg segments per warp at a time: longer episodes (a box that
+// covers hundreds of patches of a large grid) are expanded block by block -- a first pass over all segments
+// yields the episode length (only the LAST T records are kept, so it has to be known first), then every block
+// of kMaxSeg segments fills the table and writes the kept records it owns.  A record's `next_actions`
+// overwrite may come from a later block than its position; blocks run in order and a slot is always handled
+// by the same lane, so the later write wins as it does in the reference.
 constexpr int kMaxSeg = 128;
 constexpr int kTrajWarps = 4;
 
@@ -135,6 +139,51 @@ struct SegTable {
 };
 
 __device__ __forceinline__ int sgn(int v) { return (v > 0) - (v < 0); }
+
+// Phase 1 for segments [k0, k1) of an episode (a warp; lanes = segments, 32 at a time): Chebyshev lengths and
+// draw counts with running warp scans.  `table` null: totals only.  run_len / run_draw carry the prefix in and out.
+__device__ __forceinline__ void scan_segments(SegTable* table, const int32_t* __restrict__ seg_to,
+                                              const int32_t* __restrict__ seg_tgt,
+                                              const uint8_t* __restrict__ seg_flags, int s0, int k0, int k1, int sy,
+                                              int sx, int lane, int& run_len, int& run_draw) {
+  for (int base = k0; base < k1; base += 32) {
+    const int k = base + lane;
+    int L = 0, dcount = 0, hit = 0, ay = 0, ax = 0, by = 0, bx = 0, ty = 0, tx = 0, first = 0, open_draw = 0;
+    if (k < k1) {
+      by = seg_to[2 * (s0 + k)]; bx = seg_to[2 * (s0 + k) + 1];
+      ty = seg_tgt[2 * (s0 + k)]; tx = seg_tgt[2 * (s0 + k) + 1];
+      if (k == 0) { ay = sy; ax = sx; } else { ay = seg_to[2 * (s0 + k - 1)]; ax = seg_to[2 * (s0 + k - 1) + 1]; }
+      first = seg_flags[s0 + k] & 1;
+      const int dy = by - ay, dx = bx - ax;
+      L = imax(iabs(dy), iabs(dx));
+      open_draw = (first && ay == ty && ax == tx) ? 1 : 0;
+      // the walk stands on tgt at step j iff both axes agree; positions are monotone per axis
+      for (int j = 1; j <= L; ++j) {
+        const int py = ay + sgn(dy) * imin(j, iabs(dy)), px = ax + sgn(dx) * imin(j, iabs(dx));
+        if (py == ty && px == tx) { hit = j; break; }
+      }
+      dcount = open_draw + (hit ? 1 : 0);
+    }
+    // inclusive warp scans
+    int incl_len = L, incl_draw = dcount;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, incl_len, off), b = __shfl_up_sync(0xffffffffu, incl_draw, off);
+      if (lane >= off) { incl_len += a; incl_draw += b; }
+    }
+    if (table && k < k1) {
+      SegTable& s = *table;
+      const int i = k - k0;
+      s.ay[i] = (int16_t)ay; s.ax[i] = (int16_t)ax; s.by[i] = (int16_t)by; s.bx[i] = (int16_t)bx;
+      s.ty[i] = (int16_t)ty; s.tx[i] = (int16_t)tx;
+      s.len[i] = L; s.pre[i] = run_len + incl_len - L;
+      s.draw0[i] = run_draw + incl_draw - dcount;
+      s.hit[i] = (int16_t)hit; s.first[i] = (uint8_t)first; s.open_draw[i] = (uint8_t)open_draw;
+    }
+    run_len += __shfl_sync(0xffffffffu, incl_len, 31);
+    run_draw += __shfl_sync(0xffffffffu, incl_draw, 31);
+  }
+}
 
 __global__ void __launch_bounds__(kTrajWarps * 32)
 traj_expand_kernel(const int32_t* __restrict__ start_yx, const int32_t* __restrict__ seg_begin,
@@ -155,52 +204,14 @@ traj_expand_kernel(const int32_t* __restrict__ start_yx, const int32_t* __restri
     const int cols = cols_arr[e];
     const uint32_t* bm = area + (long long)e * words_per_item;
     const long long o = (long long)e * T;
-    bool bad = ns > kMaxSeg;
-    int ep_len = 1;
 
-    if (!bad) {
-      // ---- phase 1: per-segment lengths and draw counts, scanned in blocks of 32 segments
-      int run_len = 0, run_draw = 0;
-      for (int base = 0; base < ns; base += 32) {
-        const int k = base + lane;
-        int L = 0, dcount = 0, hit = 0, ay = 0, ax = 0, by = 0, bx = 0, ty = 0, tx = 0, first = 0, open_draw = 0;
-        if (k < ns) {
-          by = seg_to[2 * (s0 + k)]; bx = seg_to[2 * (s0 + k) + 1];
-          ty = seg_tgt[2 * (s0 + k)]; tx = seg_tgt[2 * (s0 + k) + 1];
-          if (k == 0) { ay = sy; ax = sx; } else { ay = seg_to[2 * (s0 + k - 1)]; ax = seg_to[2 * (s0 + k - 1) + 1]; }
-          first = seg_flags[s0 + k] & 1;
-          const int dy = by - ay, dx = bx - ax;
-          L = imax(iabs(dy), iabs(dx));
-          open_draw = (first && ay == ty && ax == tx) ? 1 : 0;
-          // the walk stands on tgt at step j iff both axes agree; positions are monotone per axis
-          for (int j = 1; j <= L; ++j) {
-            const int py = ay + sgn(dy) * imin(j, iabs(dy)), px = ax + sgn(dx) * imin(j, iabs(dx));
-            if (py == ty && px == tx) { hit = j; break; }
-          }
-          dcount = open_draw + (hit ? 1 : 0);
-        }
-        // inclusive warp scans
-        int incl_len = L, incl_draw = dcount;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-          const int a = __shfl_up_sync(0xffffffffu, incl_len, off), b = __shfl_up_sync(0xffffffffu, incl_draw, off);
-          if (lane >= off) { incl_len += a; incl_draw += b; }
-        }
-        if (k < ns) {
-          s.ay[k] = (int16_t)ay; s.ax[k] = (int16_t)ax; s.by[k] = (int16_t)by; s.bx[k] = (int16_t)bx;
-          s.ty[k] = (int16_t)ty; s.tx[k] = (int16_t)tx;
-          s.len[k] = L; s.pre[k] = run_len + incl_len - L;
-          s.draw0[k] = run_draw + incl_draw - dcount;
-          s.hit[k] = (int16_t)hit; s.first[k] = (uint8_t)first; s.open_draw[k] = (uint8_t)open_draw;
-        }
-        run_len += __shfl_sync(0xffffffffu, incl_len, 31);
-        run_draw += __shfl_sync(0xffffffffu, incl_draw, 31);
-      }
-      __syncwarp();
-      ep_len = 1 + run_len;
-      if (run_draw > nd) bad = true;  // planner supplied too few replacement moves
-    }
-    if (bad) {
+    // ---- phase 1: episode length and draw count (episodes of up to kMaxSeg segments fill the table right away)
+    const bool one_block = ns <= kMaxSeg;
+    int total_len = 0, total_draw = 0;
+    scan_segments(one_block ? &s : nullptr, seg_to, seg_tgt, seg_flags, s0, 0, ns, sy, sx, lane, total_len, total_draw);
+    __syncwarp();
+    const int ep_len = 1 + total_len;
+    if (total_draw > nd) {  // planner supplied too few replacement moves: the episode is left masked out
       if (lane == 0 && status) atomicOr(status, 8);
       for (int t = lane; t < T; t += 32) {
         positions[2 * (o + t)] = 0; positions[2 * (o + t) + 1] = 0;
@@ -211,44 +222,59 @@ traj_expand_kernel(const int32_t* __restrict__ start_yx, const int32_t* __restri
       continue;
     }
 
-    // ---- phases 2+3: one lane per kept record
+    // ---- phases 2+3: one lane per kept record, one block of segments at a time
     const int drop = ep_len > T ? ep_len - T : 0;  // keep the LAST T records (simple_env.py:580-584)
-    for (int slot = lane; slot < T; slot += 32) {
-      const int t = slot + drop;  // record index in the untruncated episode
-      if (t >= ep_len) {
-        positions[2 * (o + slot)] = 0; positions[2 * (o + slot) + 1] = 0;
-        cur_act[o + slot] = 0; next_act[o + slot] = 0; labels[o + slot] = 0; masks[o + slot] = 0.f;
-        gather_src[o + slot] = -1;
-        continue;
+    int run_len = 0, run_draw = 0;
+    for (int k0 = 0; k0 == 0 || k0 < ns; k0 += kMaxSeg) {
+      const int k1 = imin(ns, k0 + kMaxSeg), nb = k1 - k0;
+      if (!one_block) {
+        __syncwarp();  // the previous block's table has been read by every lane
+        scan_segments(&s, seg_to, seg_tgt, seg_flags, s0, k0, k1, sy, sx, lane, run_len, run_draw);
+        __syncwarp();
       }
-      int py = sy, px = sx, act = 0 /*LEFT placeholder, simple_env.py:527-534*/, best = 0;
-      // owning segment: records of segment k are t = pre_k + j, j = 1..len_k
-      // overwrite: the last group-opening segment with pre_k == t rewrites next_actions[t]
-      int own = -1, over = -1;
-      for (int k = 0; k < ns; ++k) {
-        const int pre = s.pre[k];
-        if (t > pre && t <= pre + s.len[k]) own = k;
-        if (s.first[k] && pre == t) over = k;
+      for (int slot = lane; slot < T; slot += 32) {
+        const int t = slot + drop;  // record index in the untruncated episode
+        if (t >= ep_len) {
+          if (k0 == 0) {
+            positions[2 * (o + slot)] = 0; positions[2 * (o + slot) + 1] = 0;
+            cur_act[o + slot] = 0; next_act[o + slot] = 0; labels[o + slot] = 0; masks[o + slot] = 0.f;
+            gather_src[o + slot] = -1;
+          }
+          continue;
+        }
+        // owning segment: records of segment k are t = pre_k + j, j = 1..len_k (the start record t = 0 has none)
+        // overwrite: the last group-opening segment with pre_k == t rewrites next_actions[t]
+        int own = -1, over = -1;
+        for (int i = 0; i < nb; ++i) {
+          const int pre = s.pre[i];
+          if (t > pre && t <= pre + s.len[i]) own = i;
+          if (s.first[i] && pre == t) over = i;
+        }
+        const bool start_record = (t == 0 && k0 == 0);
+        if (own >= 0 || start_record) {
+          int py = sy, px = sx, act = 0 /*LEFT placeholder, simple_env.py:527-534*/, best = 0;
+          if (own >= 0) {
+            const int j = t - s.pre[own];
+            const int dy = s.by[own] - s.ay[own], dx = s.bx[own] - s.ax[own];
+            const int qy = s.ay[own] + sgn(dy) * imin(j - 1, iabs(dy)), qx = s.ax[own] + sgn(dx) * imin(j - 1, iabs(dx));
+            py = s.ay[own] + sgn(dy) * imin(j, iabs(dy)); px = s.ax[own] + sgn(dx) * imin(j, iabs(dx));
+            act = direction_code(s.by[own] - qy, s.bx[own] - qx);
+            best = direction_code(s.ty[own] - py, s.tx[own] - px);
+            if (best == kStop) best = draws[d0 + s.draw0[own] + s.open_draw[own]];  // j == hit[own]
+          }
+          const int bit = py * cols + px;
+          positions[2 * (o + slot)] = py; positions[2 * (o + slot) + 1] = px;
+          cur_act[o + slot] = act; next_act[o + slot] = best;
+          labels[o + slot] = (bm[bit >> 5] >> (bit & 31)) & 1u;
+          masks[o + slot] = 1.0f;
+          gather_src[o + slot] = e;
+        }
+        if (over >= 0) {
+          int best = direction_code(s.ty[over] - s.ay[over], s.tx[over] - s.ax[over]);
+          if (best == kStop) best = draws[d0 + s.draw0[over]];
+          next_act[o + slot] = best;
+        }
       }
-      if (own >= 0) {
-        const int j = t - s.pre[own];
-        const int dy = s.by[own] - s.ay[own], dx = s.bx[own] - s.ax[own];
-        const int qy = s.ay[own] + sgn(dy) * imin(j - 1, iabs(dy)), qx = s.ax[own] + sgn(dx) * imin(j - 1, iabs(dx));
-        py = s.ay[own] + sgn(dy) * imin(j, iabs(dy)); px = s.ax[own] + sgn(dx) * imin(j, iabs(dx));
-        act = direction_code(s.by[own] - qy, s.bx[own] - qx);
-        best = direction_code(s.ty[own] - py, s.tx[own] - px);
-        if (best == kStop) best = draws[d0 + s.draw0[own] + s.open_draw[own]];  // j == hit[own]
-      }
-      if (over >= 0) {
-        best = direction_code(s.ty[over] - s.ay[over], s.tx[over] - s.ax[over]);
-        if (best == kStop) best = draws[d0 + s.draw0[over]];
-      }
-      const int bit = py * cols + px;
-      positions[2 * (o + slot)] = py; positions[2 * (o + slot) + 1] = px;
-      cur_act[o + slot] = act; next_act[o + slot] = best;
-      labels[o + slot] = (bm[bit >> 5] >> (bit & 31)) & 1u;
-      masks[o + slot] = 1.0f;
-      gather_src[o + slot] = e;
     }
     if (lane == 0) ep_len_out[e] = ep_len;
     __syncwarp();

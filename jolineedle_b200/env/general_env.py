@@ -25,12 +25,14 @@ Extensions (keyword-only, default = reference behaviour):
              zero-padded at the bottom / right (``padded_collate_fn``, dataset.py:307-347) without
              materialising the padding (the TMA unit zero-fills what lies outside the image)
 """
+import ctypes
 from typing import List, Optional, Tuple
 
 import torch
 from torch import Tensor
 
 from .. import _cabi
+from .. import gather as _gather_mod
 from ..gather import ImageSet
 from .common import Action, ACTION_DELTAS, DELTA_TABLE  # noqa: F401  (re-exported like the reference module)
 
@@ -135,16 +137,36 @@ class NeedleGeneralEnv:
             slots = self._history.shape[1]
             self._history_set = ImageSet(self._history.view((self.batch_size * slots,) + tuple(self._history.shape[2:])),
                                          self._history.shape[-1])  # one-patch images (P, or P/2 in the Focus layout)
-            self._origin = torch.zeros((self.batch_size, 2), dtype=torch.long, device=self.device)
         self.host_tiles = torch.zeros((), dtype=torch.long, device=self.device)  # tiles read over PCIe so far
         if n_glimps_levels > 1:
             levels = n_glimps_levels
             ids = torch.arange(self.batch_size * levels, dtype=torch.int32, device=self.device)
             self._level_src = [ids[l::levels].contiguous() for l in range(levels)]  # image b*G + l of level l
         self._t = 0
-        self._launch_gather = None  # bound K1 launch of the one-level step gather (see _gather)
+        self._launch_gather = None  # bound K1 launch of the stand-alone one-level gather (see _gather)
         self._tile_shape = self._set.out_shape(self.batch_size, focus)
         self._tile_dtype = self._set.out_dtype(normalize)
+        elem = 4 if self._tile_dtype == torch.float32 else 1
+        tile_bytes = elem * self._tile_shape[1] * self._tile_shape[2] * self._tile_shape[3]
+        # one native call per step (jn_env_step_gather): argument block filled once, per-step fields rewritten
+        self._fused = n_glimps_levels == 1
+        self._args = _cabi.EnvStepArgs()
+        self._args_ref = ctypes.byref(self._args)
+        a = self._args
+        a.n, a.rows, a.cols = self.batch_size, self.n_vertical_patches, self.n_horizontal_patches
+        a.max_ep_len, a.stop_enabled, a.cost = max_ep_len, 1 if stop_enabled else 0, self._cost
+        a.bbox, a.status = self._bbox_words.data_ptr(), self._status.data_ptr()
+        a.slots = self._history.shape[1] if self._history is not None else 1
+        a.shifts = _cabi.ptr(self._shifts)
+        a.flags = ((_cabi.GATHER_NORMALIZE if normalize else 0) | (_cabi.GATHER_FOCUS if focus else 0)
+                   | (_cabi.GATHER_SHIFT_ALIGNED if (self._shifts is not None and self._shifts_aligned) else 0))
+        a.engine = _cabi.ENGINES[engine]
+        a.out_item_stride_bytes = tile_bytes * (a.slots if self._history is not None else 1)
+        a.host_tiles = self.host_tiles.data_ptr() if self._history_set is not None else None
+        self._set_handle = self._set._handle if self._fused else None
+        self._hist_handle = self._history_set._handle if self._history_set is not None else None
+        # [B, 1, C, P, P] views of the history slots, made on first use
+        self._slot_views: List[Optional[Tensor]] = [None] * (a.slots if self._history is not None else 0)
         self.init_env_variables()
 
     @torch.no_grad()
@@ -184,16 +206,53 @@ class NeedleGeneralEnv:
     def visited_patches(self) -> Tensor:
         return self._unpack(self._visited_words)
 
-    def init_env_variables(self):  # general_env.py:117-142
-        b, dev = self.batch_size, self.device
-        self.positions = torch.zeros((b, 2), dtype=torch.long, device=dev)
-        self._visited_words = torch.zeros((b, self._words), dtype=torch.int32, device=dev)
-        self.steps = torch.zeros((b,), dtype=torch.long, device=dev)
-        self.has_stopped = torch.zeros((b,), dtype=torch.bool, device=dev)
+    def init_env_variables(self, zero: bool = True):  # general_env.py:117-142
+        """Fresh episode state.  Per-step results live in step-major rings allocated here -- row t of
+        ``[max_ep_len, B]`` rewards / terminated / truncated and of ``[max_ep_len + 1, B, 2]`` positions is what
+        step t returns -- so a step allocates nothing, and tensors handed out during one episode are never
+        overwritten by the next (``reset`` takes new rings).  ``zero=False``: the reset kernel is about to
+        overwrite the state, skip the memsets."""
+        b, dev, words = self.batch_size, self.device, self._words
+        make = torch.zeros if zero else torch.empty
+        self._visited_words = make((b, words), dtype=torch.int32, device=dev)
+        self.steps = make((b,), dtype=torch.long, device=dev)
+        self.has_stopped = make((b,), dtype=torch.bool, device=dev)
         self._t = 0
-        if getattr(self, "_history_set", None) is not None:
-            self._first_slot = torch.full((b, self.n_vertical_patches * self.n_horizontal_patches), -1,
-                                          dtype=torch.int32, device=dev)
+        if self._history_set is not None:
+            self._first_slot = torch.empty((b, self.n_vertical_patches * self.n_horizontal_patches),
+                                           dtype=torch.int32, device=dev)
+            if zero:
+                self._first_slot.fill_(-1)
+            self._host_src = torch.empty((b,), dtype=torch.int32, device=dev)
+            self._hist_src = torch.empty((b,), dtype=torch.int32, device=dev)
+        self._new_rings(zero)
+        a = self._args
+        a.visited, a.steps, a.has_stopped = self._visited_words.data_ptr(), self.steps.data_ptr(), self.has_stopped.data_ptr()
+        if self._history_set is not None:
+            a.first_slot, a.host_src, a.history_src = (self._first_slot.data_ptr(), self._host_src.data_ptr(),
+                                                       self._hist_src.data_ptr())
+
+    def _new_rings(self, zero: bool = False):
+        b, dev, n = self.batch_size, self.device, self.max_ep_len
+        self._pos_ring = (torch.zeros if zero else torch.empty)((n + 1, b, 2), dtype=torch.long, device=dev)
+        self._rew_ring = torch.empty((n, b), dtype=torch.float32, device=dev)
+        self._term_ring = torch.empty((n, b), dtype=torch.bool, device=dev)
+        self._trunc_ring = torch.empty((n, b), dtype=torch.bool, device=dev)
+        # one C++ call per ring instead of one python slicing per step and tensor
+        self._pos_rows, self._rew_rows = self._pos_ring.unbind(0), self._rew_ring.unbind(0)
+        self._term_rows, self._trunc_rows = self._term_ring.unbind(0), self._trunc_ring.unbind(0)
+        self._pos_base, self._rew_base = self._pos_ring.data_ptr(), self._rew_ring.data_ptr()
+        self._term_base, self._trunc_base = self._term_ring.data_ptr(), self._trunc_ring.data_ptr()
+        self._ring_k = 0  # rows of the ring used so far (row k of the positions = state after k steps)
+        self.positions = self._cur_row = self._pos_rows[0]
+
+    def rollout_buffers(self) -> Tuple[Tensor, Tensor, Tensor]:
+        """Step-major ``[t, B]`` rewards / terminated / truncated of the steps taken since ``reset`` (views of
+        the rings; ``jolineedle_b200.reinforce.rollout_tail`` consumes them as they are -- no per-step stacking)."""
+        k = self._ring_k
+        if k != self._t:
+            raise RuntimeError("the episode ran past max_ep_len: the rings only hold its last steps")
+        return self._rew_ring[:k], self._term_ring[:k], self._trunc_ring[:k]
 
     def check_status(self):
         """Synchronise and raise if a kernel flagged invalid input (the reference raises at the
@@ -207,7 +266,16 @@ class NeedleGeneralEnv:
             raise IndexError("a bounding box falls outside the patch grid")
 
     # ------------------------------------------------------------------------------------
+    def _slot(self, t: int) -> Tensor:
+        """``[B, 1, C, P, P]`` view of history slot ``t``."""
+        v = self._slot_views[t]
+        if v is None:
+            v = self._slot_views[t] = self._history[:, t:t + 1]
+        return v
+
     def _gather(self) -> Tensor:
+        """Stand-alone gather at the current positions (the ``patches`` property, general_env.py:285-306; reset
+        and step gather inside their own native call)."""
         if self.n_glimps_levels > 1:
             return self._gather_levels()
         if self._history is not None:
@@ -216,15 +284,15 @@ class NeedleGeneralEnv:
             out = torch.empty(self._tile_shape, dtype=self._tile_dtype, device=self.device)
         if self._history_set is not None:
             return self._gather_zero_copy(out).unsqueeze(1)
-        if self._launch_gather is None:  # argument checks once per env, not once per step
+        if self._launch_gather is None:  # argument checks once per env, not once per call
             self._launch_gather = self._set.bind(normalize=self._normalize, focus=self._focus, engine=self._engine,
                                                  status=self._status, tag="step", shifts=self._shifts,
                                                  shifts_aligned=self._shifts_aligned)
         return self._launch_gather(self.positions, out).unsqueeze(1)  # [B, G=1, C, P, P]
 
     def _gather_zero_copy(self, out: Tensor) -> Tensor:
-        """Slot ``t`` of the history from pinned host images: patches seen for the first time come over PCIe,
-        revisited ones are copied from the slot that first held them."""
+        """Slot ``t`` of the history from pinned host images, outside of a step: patches seen for the first time
+        come over PCIe, revisited ones are copied from the slot that first held them."""
         b, dev = self.batch_size, self.device
         host_src = torch.empty((b,), dtype=torch.int32, device=dev)
         hist_src = torch.empty((b,), dtype=torch.int32, device=dev)
@@ -236,7 +304,7 @@ class NeedleGeneralEnv:
         self._set.gather(self.positions, src_index=host_src, out=out, normalize=self._normalize, focus=self._focus,
                          engine=self._engine, status=self._status, tag="step", shifts=self._shifts,
                          shifts_aligned=self._shifts_aligned)
-        self._history_set.gather(self._origin, src_index=hist_src, out=out, engine=self._engine, status=self._status,
+        self._history_set.gather(None, src_index=hist_src, out=out, engine=self._engine, status=self._status,
                                  tag="step-reuse")
         self.host_tiles += (host_src >= 0).sum()
         return out
@@ -265,45 +333,86 @@ class NeedleGeneralEnv:
             raise RuntimeError("construct the env with history=True to keep the crop history")
         return self._history[:, : ((self._t if upto is None else upto) + 1) * self.n_glimps_levels]
 
+    def _call(self, fn, out: Optional[Tensor]):
+        """One native call: state kernel + the gather of ``out`` behind it (events around it when bench.py asked
+        for per-launch timings)."""
+        a = self._args
+        a.out = None if out is None else out.data_ptr()
+        timing = _gather_mod.TIMING
+        with _cabi.on_device(self.device):
+            pair = timing.begin() if (timing is not None and out is not None) else None
+            rc = fn(self._set_handle, self._hist_handle, self._args_ref, _cabi.stream_ptr(self.device))
+            if pair is not None:
+                timing.end(pair, "step", self.batch_size)
+        if rc:
+            _cabi.check(rc)
+
+    def _crop_buffer(self, t: int) -> Tuple[Optional[Tensor], Tensor]:
+        """(tensor the fused gather writes, ``[B, G, C, P, P]`` tensor handed to the caller) for slot ``t``."""
+        if not self._fused:
+            return None, None
+        if self._history is not None:
+            if t >= len(self._slot_views):
+                raise RuntimeError(f"history=True keeps max_ep_len + 1 = {len(self._slot_views)} crops per episode; "
+                                   f"step {t} does not fit (reset the env or build it without history)")
+            view = self._slot(t)
+            return view, view
+        out = torch.empty(self._tile_shape, dtype=self._tile_dtype, device=self.device)
+        return out, out.unsqueeze(1)
+
     def reset(self, positions: Optional[Tensor] = None) -> Tuple[Tensor, dict]:  # general_env.py:144-170
-        self.init_env_variables()
+        self.init_env_variables(zero=False)
+        row0 = self._pos_rows[0]
         if positions is not None:
-            self.positions = positions.to(device=self.device, dtype=torch.long).contiguous()
+            assert tuple(positions.shape) == (self.batch_size, 2)
+            row0.copy_(positions, non_blocking=True)
         else:
             # host RNG in the reference's order: rows first, then columns, CPU default generator
             ys = torch.randint(low=0, high=self.n_vertical_patches, size=(self.batch_size,))
             xs = torch.randint(low=0, high=self.n_horizontal_patches, size=(self.batch_size,))
             staged = torch.empty((self.batch_size, 2), dtype=torch.long, pin_memory=True)
             torch.stack((ys, xs), dim=1, out=staged)  # pinned staging: the upload does not wait for the stream
-            self.positions = staged.to(self.device, non_blocking=True)
-        assert tuple(self.positions.shape) == (self.batch_size, 2)
-        with _cabi.on_device(self.device):
-            _cabi.check(self._lib.jn_env_reset(
-                self.positions.data_ptr(), self._visited_words.data_ptr(), self.steps.data_ptr(),
-                self.has_stopped.data_ptr(), self.batch_size, self.n_vertical_patches, self.n_horizontal_patches,
-                self._status.data_ptr(), self._stream()))
-        infos = {"positions": self.positions}
-        return self._gather(), infos
+            row0.copy_(staged, non_blocking=True)
+        a = self._args
+        a.pos_out, a.t = self._pos_base, 0
+        if self._history_set is not None:
+            self.host_tiles.zero_()
+        out, patches = self._crop_buffer(0)
+        self._call(self._lib.jn_env_reset_gather, out)
+        if not self._fused:
+            patches = self._gather()
+        return patches, {"positions": self.positions}
 
     def step(self, actions: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor, dict]:  # general_env.py:172-207
         b, dev = self.batch_size, self.device
-        actions = actions.to(device=dev, dtype=torch.long).contiguous()
+        if actions.dtype != torch.long or actions.device != dev or not actions.is_contiguous():
+            actions = actions.to(device=dev, dtype=torch.long).contiguous()
         assert actions.numel() == b
-        new_positions = torch.empty((b, 2), dtype=torch.long, device=dev)
-        rewards = torch.empty((b,), dtype=torch.float32, device=dev)
-        terminated = torch.empty((b,), dtype=torch.bool, device=dev)
-        truncated = torch.empty((b,), dtype=torch.bool, device=dev)
-        with _cabi.on_device(dev):
-            _cabi.check(self._lib.jn_env_step(
-                self.positions.data_ptr(), actions.data_ptr(), new_positions.data_ptr(),
-                self._visited_words.data_ptr(), self._bbox_words.data_ptr(), self.steps.data_ptr(),
-                self.has_stopped.data_ptr(), rewards.data_ptr(), terminated.data_ptr(), truncated.data_ptr(), b,
-                self.n_vertical_patches, self.n_horizontal_patches, self.max_ep_len, self._cost,
-                1 if self.stop_enabled else 0, self._status.data_ptr(), self._stream()))
-        self.positions = new_positions
+        k = self._ring_k
+        if k >= self.max_ep_len:  # stepping past max_ep_len (truncated stays True): continue in fresh rings
+            cur = self.positions
+            self._new_rings()
+            self._pos_rows[0].copy_(cur)
+            self.positions = self._cur_row = self._pos_rows[0]
+            k = 0
+        pos = self.positions
+        if pos is not self._cur_row:  # someone rebound env.positions (apply_movements): take it as it is
+            pos = self.positions = pos.to(device=dev, dtype=torch.long).contiguous()
+        a = self._args
+        a.pos_in, a.actions = pos.data_ptr(), actions.data_ptr()
+        a.pos_out = self._pos_base + (k + 1) * b * 16
+        a.rewards = self._rew_base + k * b * 4
+        a.terminated, a.truncated = self._term_base + k * b, self._trunc_base + k * b
+        a.t = self._t + 1
+        out, patches = self._crop_buffer(self._t + 1)
+        self._call(self._lib.jn_env_step_gather, out)
+        self._keep_actions = actions  # the kernels read it after this call returns
         self._t += 1
-        infos = {"positions": self.positions}
-        return self._gather(), rewards, terminated, truncated, infos
+        self._ring_k = k + 1
+        self.positions = self._cur_row = self._pos_rows[k + 1]
+        if not self._fused:
+            patches = self._gather()
+        return patches, self._rew_rows[k], self._term_rows[k], self._trunc_rows[k], {"positions": self.positions}
 
     # ------------------------------------------------------------------------------------
     def _props(self, want_prop: bool, want_term: bool):

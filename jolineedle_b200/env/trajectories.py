@@ -31,31 +31,43 @@ class PackedPlans:
     """Flat host arrays describing ``n`` planned episodes (see ``jn_traj_expand``)."""
 
     __slots__ = ("n", "start", "seg_begin", "seg_to", "seg_tgt", "seg_flags", "draw_begin", "draws", "det_begin",
-                 "det_yx", "rows", "cols", "n_boxes", "boxes", "n_max")
+                 "det_yx", "rows", "cols", "n_boxes", "boxes", "n_max", "boxes_f64")
+
+    def __init__(self):
+        self.boxes_f64 = None  # [n, n_max, 4] float64 when some box coordinate is not a whole pixel
 
 
 # ---------------------------------------------------------------------------------------------------
 # python planner -> packed
 # ---------------------------------------------------------------------------------------------------
-def boxes_array(bboxes: Sequence[Sequence], n_max: Optional[int] = None):
+def boxes_array(bboxes: Sequence[Sequence], n_max: Optional[int] = None, want_float: bool = False):
     """``[n, max(n_max, 1), 4]`` int64 x1,y1,x2,y2 + per-image counts; ``exact`` tells whether every
-    coordinate was an integer (the native planner and the kernels work on integer pixels)."""
+    coordinate was an integer (the native planner works on integer pixels).  ``want_float``: a fifth value,
+    the same array in float64 when the boxes are not exact (None otherwise) -- the reference keeps such boxes
+    as python floats (the dataset's minimum-size resize scales them, dataset.py:258-270), so labels and local
+    boxes must come from the un-truncated coordinates."""
     n = len(bboxes)
     counts = np.array([len(b) for b in bboxes], dtype=np.int32)
     n_max = int(counts.max()) if n_max is None and n else (n_max or 0)
     arr = np.zeros((n, max(n_max, 1), 4), dtype=np.int64)
     total = int(counts.sum())
     if total == 0:
-        return arr, counts, n_max, True
+        return (arr, counts, n_max, True, None) if want_float else (arr, counts, n_max, True)
     # one conversion for the whole batch: BBox = ((y1, x1), (y2, x2)) -> flat list of 4 * total numbers
     # (flattening in python first is ~10x faster than letting numpy walk the nested tuples)
     flat = np.array(list(_chain(_chain(_chain(bboxes)))))
     exact = bool(np.issubdtype(flat.dtype, np.integer)) or bool(np.all(flat == np.floor(flat)))
-    flat = flat.reshape(total, 4)[:, [1, 0, 3, 2]].astype(np.int64)  # -> x1, y1, x2, y2 (truncation like `.int()`)
+    flat = flat.reshape(total, 4)[:, [1, 0, 3, 2]]  # -> x1, y1, x2, y2
     image = np.repeat(np.arange(n), counts)
     slot = np.arange(total) - np.repeat(np.cumsum(counts) - counts, counts)
-    arr[image, slot] = flat
-    return arr, counts, n_max, exact
+    arr[image, slot] = flat.astype(np.int64)  # (truncation like `.int()`; only used when exact)
+    if not want_float:
+        return arr, counts, n_max, exact
+    arr_f = None
+    if not exact:
+        arr_f = np.zeros(arr.shape, dtype=np.float64)
+        arr_f[image, slot] = flat.astype(np.float64)
+    return arr, counts, n_max, exact, arr_f
 
 
 def pack_python_plans(envs, plans) -> PackedPlans:
@@ -78,7 +90,7 @@ def pack_python_plans(envs, plans) -> PackedPlans:
     p.det_yx = np.array([c for pl in plans for c in pl.det_positions], dtype=np.int32).reshape(n_det, 2)
     p.rows = np.array([e.patch_height for e in envs], dtype=np.int32)
     p.cols = np.array([e.patch_width for e in envs], dtype=np.int32)
-    p.boxes, p.n_boxes, p.n_max, _ = boxes_array([e.raw_bboxes for e in envs])
+    p.boxes, p.n_boxes, p.n_max, _, p.boxes_f64 = boxes_array([e.raw_bboxes for e in envs], want_float=True)
     return p
 
 
@@ -227,6 +239,11 @@ def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normaliz
     u8 = np.concatenate([p.seg_flags, p.draws, np.zeros(1, dtype=np.uint8)])
     i64 = np.concatenate([p.boxes.ravel(), p.det_yx.astype(np.int64).ravel()])
     d_i32, d_u8, d_i64 = (_upload(a, dev) for a in (i32, u8, i64))
+    # boxes that are not whole pixels: labels and local boxes from the float64 coordinates (python planner only)
+    float_boxes = p.boxes_f64 is not None
+    d_boxes_f64 = _upload(p.boxes_f64, dev) if float_boxes else None
+    patch_bitmaps = lib.jn_patch_bitmaps_f64 if float_boxes else lib.jn_patch_bitmaps
+    local_boxes = lib.jn_local_boxes_f64 if float_boxes else lib.jn_local_boxes
 
     o = 0
 
@@ -240,7 +257,7 @@ def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normaliz
     d_seg_to, d_seg_tgt = take(2 * n_seg), take(2 * n_seg)
     d_draw_begin, d_rows, d_cols, d_nboxes, d_det_src = take(n + 1), take(n), take(n), take(n), take(n_det)
     d_flags, d_draws = d_u8[:n_seg], d_u8[n_seg:n_seg + n_draw + 1]
-    d_boxes = d_i64[:p.boxes.size].view(p.boxes.shape)
+    d_boxes = d_boxes_f64 if float_boxes else d_i64[:p.boxes.size].view(p.boxes.shape)
     d_det_pos = d_i64[p.boxes.size:].view(n_det, 2)
 
     words = int(((p.rows.astype(np.int64) * p.cols + 31) // 32).max())
@@ -260,7 +277,7 @@ def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normaliz
     ep_len = torch.empty((n,), dtype=torch.int32, device=dev)
     with _cabi.on_device(dev):
         # K0: 5 %-area bitmaps (labels = inside_bbox, simple_env.py:225,478)
-        _cabi.check(lib.jn_patch_bitmaps(d_boxes.data_ptr(), d_nboxes.data_ptr(), n, p.boxes.shape[1], P, 0, 0,
+        _cabi.check(patch_bitmaps(d_boxes.data_ptr(), d_nboxes.data_ptr(), n, p.boxes.shape[1], P, 0, 0,
                                          d_rows.data_ptr(), d_cols.data_ptr(), _cabi.RULE_AREA5, area.data_ptr(),
                                          words, stream))
         # K3: plan -> per-step records
@@ -272,9 +289,9 @@ def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normaliz
             gather_src.data_ptr(), ep_len.data_ptr(), status.data_ptr(), stream))
         # per-step local boxes (simple_env.py:479)
         if n_max > 0:
-            _cabi.check(lib.jn_local_boxes(d_boxes.data_ptr(), d_nboxes.data_ptr(), n_max, P,
-                                           out["positions"].data_ptr(), gather_src.data_ptr(), n * T,
-                                           out["local_bboxes"].data_ptr(), stream))
+            _cabi.check(local_boxes(d_boxes.data_ptr(), d_nboxes.data_ptr(), n_max, P,
+                                    out["positions"].data_ptr(), gather_src.data_ptr(), n * T,
+                                    out["local_bboxes"].data_ptr(), stream))
     # K1: the glimpses themselves, straight into [B, T, C, P, P]; padded slots are zero-filled
     traj_tiles = out["patches"].view((n * T,) + out["patches"].shape[2:])
     reuse_set = None
@@ -290,8 +307,8 @@ def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normaliz
                                            first_src.data_ptr(), repeat_src.data_ptr(), stream))
         image_set.gather(out["positions"].view(n * T, 2), src_index=first_src, out=traj_tiles, normalize=normalize,
                          engine=engine, status=status, tag="trajectory")
-        reuse_set.gather(torch.zeros((n * T, 2), dtype=torch.long, device=dev), src_index=repeat_src, out=traj_tiles,
-                         engine=engine, status=status, tag="trajectory-reuse")
+        reuse_set.gather(None, src_index=repeat_src, out=traj_tiles, engine=engine, status=status,
+                         tag="trajectory-reuse")
         out["_host_traj_tiles"] = (first_src >= 0).sum()  # trajectory tiles that did cross PCIe
     else:
         image_set.gather(out["positions"].view(n * T, 2), src_index=gather_src.view(n * T), out=traj_tiles,
@@ -331,8 +348,8 @@ def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normaliz
     det_boxes = torch.empty((n_det, n_max, 6), dtype=torch.float32, device=dev)
     if n_max > 0 and n_det > 0:
         with _cabi.on_device(dev):
-            _cabi.check(lib.jn_local_boxes(d_boxes.data_ptr(), d_nboxes.data_ptr(), n_max, P, d_det_pos.data_ptr(),
-                                           d_det_src.data_ptr(), n_det, det_boxes.data_ptr(), stream))
+            _cabi.check(local_boxes(d_boxes.data_ptr(), d_nboxes.data_ptr(), n_max, P, d_det_pos.data_ptr(),
+                                    d_det_src.data_ptr(), n_det, det_boxes.data_ptr(), stream))
     out["bboxes_yolox"] = det_boxes
     out["_ep_len"] = ep_len
     out["_status"] = status
@@ -394,12 +411,15 @@ def generate_trajectories(
     planner: str = "auto",
     zero_copy: bool = True,
     stats: Optional[dict] = None,
+    check: bool = False,
 ) -> Dict[str, torch.Tensor]:
     """Batched supervised trajectories (``SupervisedTrainer.generate_trajectories``,
     supervised.py:95-136): ``batch`` holds lists ``image`` ([C,H,W] tensors), ``bboxes`` (lists
     of ``BBox``) and ``class_id``.  Returns the collated dict of the reference on the GPU.
     ``seeds`` (one per image) makes the plans reproducible; the reference builds unseeded envs.
-    CPU images are uploaded to ``device`` first (there is no CPU path)."""
+    CPU images are uploaded to ``device`` first (there is no CPU path).  ``check`` synchronises and raises if
+    a kernel flagged its input (a position outside the grid, a plan the expansion could not follow); without it
+    the flags travel in ``stats["status"]`` and nothing waits for the device."""
     images: List[torch.Tensor] = list(batch["image"])
     if device is not None:
         # Pinned host images are NOT uploaded: a supervised episode looks at ~10 of an image's 30
@@ -417,6 +437,12 @@ def generate_trajectories(
     class_id = np.array([int(c) for c in batch["class_id"]], dtype=np.int64)
     out["class_id"] = _upload(class_id, image_set.device)
     diagnostics = {k: out.pop(k) for k in [k for k in out if k.startswith("_")]}
+    if check:
+        flags = int(diagnostics["_status"].item())
+        if flags & _cabi.STATUS_BAD_PLAN:
+            raise RuntimeError("trajectory expansion rejected a plan (fewer replacement moves than the walk needs)")
+        if flags & _cabi.STATUS_BAD_POSITION:
+            raise IndexError("a planned position lies outside its image's patch grid")
     if stats is not None:  # device scalars / tensors for benchmarks: untruncated lengths, tiles read from the host
         stats.update({k[1:]: v for k, v in diagnostics.items()})
     return out

@@ -12,9 +12,30 @@ import torch
 
 from . import _cabi
 
-# Optional per-launch timing of the gather (bench.py's roofline leg): when a list is installed
-# here, every gather appends (tag, n_items, start_event, end_event) recorded on the launch stream.
-TIMING: Optional[list] = None
+class LaunchTimer:
+    """Per-launch timing of the gathers (bench.py's roofline leg): CUDA events recorded on the launch stream
+    right around each gather call, taken from a pool created up front so that the timed region does not pay
+    for event construction.  ``records`` holds ``(tag, n_items, start_event, end_event)``."""
+
+    def __init__(self, capacity: int = 0):
+        self.pool = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                     for _ in range(capacity)]
+        self.records: list = []
+
+    def begin(self):
+        k = len(self.records)
+        pair = self.pool[k] if k < len(self.pool) else (torch.cuda.Event(enable_timing=True),
+                                                        torch.cuda.Event(enable_timing=True))
+        pair[0].record()
+        return pair
+
+    def end(self, pair, tag: str, n_items: int):
+        pair[1].record()
+        self.records.append((tag, n_items, pair[0], pair[1]))
+
+
+# When a LaunchTimer is installed here, every gather is bracketed by a pair of its events.
+TIMING: Optional[LaunchTimer] = None
 
 
 class ImageSet:
@@ -130,14 +151,11 @@ class ImageSet:
             stride = (out.stride(0) if n > 1 else out[0].numel()) * out.element_size()
             timing = TIMING
             with _cabi.on_device(device):
-                if timing is not None:
-                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    ev0.record()
+                pair = timing.begin() if timing is not None else None
                 rc = lib.jn_gather(handle, positions.data_ptr(), None, p_shifts, n, out.data_ptr(), stride, flags, code,
                                    p_status, _cabi.stream_ptr(device))
-                if timing is not None:
-                    ev1.record()
-                    timing.append((tag, n, ev0, ev1))
+                if pair is not None:
+                    timing.end(pair, tag, n)
             if rc:
                 _cabi.check(rc)
             return out
@@ -147,7 +165,7 @@ class ImageSet:
 
     def gather(
         self,
-        positions: torch.Tensor,
+        positions: Optional[torch.Tensor],
         src_index: Optional[torch.Tensor] = None,
         out: Optional[torch.Tensor] = None,
         normalize: bool = False,
@@ -162,11 +180,16 @@ class ImageSet:
         """Tile ``positions[i] = (y, x)`` of image ``src_index[i]`` (default ``i``; negative =
         zeros) -> ``out[i]``.  ``out`` may be any tensor whose ``out[i]`` is contiguous (e.g. a
         time slot ``history[:, t]`` of a ``[B, T, C, P, P]`` buffer)."""
-        _cabi.require_cuda(positions, "positions")
-        if positions.dtype != torch.int64 or positions.dim() != 2 or positions.shape[1] != 2:
-            raise ValueError("positions must be a LongTensor of shape [n, 2]")
-        positions = positions.contiguous()
-        n = positions.shape[0]
+        if positions is None:  # patch (0, 0) of every item's image: sets of one-patch images
+            if src_index is None:
+                raise ValueError("positions=None needs src_index (one one-patch image per item)")
+            n = src_index.numel()
+        else:
+            _cabi.require_cuda(positions, "positions")
+            if positions.dtype != torch.int64 or positions.dim() != 2 or positions.shape[1] != 2:
+                raise ValueError("positions must be a LongTensor of shape [n, 2]")
+            positions = positions.contiguous()
+            n = positions.shape[0]
         if src_index is not None:
             if src_index.dtype != torch.int32 or src_index.numel() != n:
                 raise ValueError("src_index must be an int32 tensor with one entry per position")
@@ -192,16 +215,13 @@ class ImageSet:
         stride = out.stride(0) * out.element_size() if n > 1 else out[0].numel() * out.element_size() if n else 0
         timing = TIMING
         with _cabi.on_device(self.device):
-            if timing is not None:
-                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                ev0.record()
+            pair = timing.begin() if timing is not None else None
             rc = _cabi.lib().jn_gather(
-                self._handle, positions.data_ptr(), _cabi.ptr(src_index), _cabi.ptr(shifts), n, out.data_ptr(), stride,
+                self._handle, _cabi.ptr(positions), _cabi.ptr(src_index), _cabi.ptr(shifts), n, out.data_ptr(), stride,
                 flags,
                 _cabi.ENGINES[engine], _cabi.ptr(status), _cabi.stream_ptr(self.device),
             )
-            if timing is not None:
-                ev1.record()
-                timing.append((tag, n, ev0, ev1))
+            if pair is not None:
+                timing.end(pair, tag, n)
         _cabi.check(rc)
         return out

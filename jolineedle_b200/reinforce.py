@@ -82,8 +82,6 @@ def rollout(
     b, t_max, dev = env.batch_size, env.max_ep_len, env.device
     actions = torch.zeros((b, t_max + 1), dtype=torch.long, device=dev)
     positions = torch.zeros((b, t_max + 1, 2), dtype=torch.long, device=dev)
-    rewards_tn = torch.empty((t_max, b), dtype=torch.float32, device=dev)
-    terminated_tn = torch.empty((t_max, b), dtype=torch.bool, device=dev)
     logprobs_tn = torch.empty((t_max, b), dtype=torch.float32, device=dev)
     entropies_tn = torch.empty((t_max, b), dtype=torch.float32, device=dev)
     classes = torch.zeros((b,), dtype=torch.int64, device=dev)
@@ -96,9 +94,8 @@ def rollout(
         hist = env.patch_history(step_id) if keep_history else patches
         logits, embeddings = policy(hist, actions[:, : step_id + 1], classes, positions[:, : step_id + 1], embeddings)
         new_actions, logprobs, entropies = sample_from_logits(logits, take_best_action=not sample_actions)
+        # (the env keeps each step's rewards / flags in step-major rings: nothing to stack here)
         new_patches, step_rewards, terminated, truncated, infos = env.step(new_actions)
-        rewards_tn[step_id] = step_rewards
-        terminated_tn[step_id] = terminated
         logprobs_tn[step_id] = logprobs
         entropies_tn[step_id] = entropies
         actions[:, step_id + 1] = new_actions
@@ -108,7 +105,8 @@ def rollout(
         steps = step_id + 1
         if early_exit and bool(torch.all(terminated | truncated)):
             break
-    tail = rollout_tail(rewards_tn[:steps], terminated_tn[:steps])
+    rewards_tn, terminated_tn, _ = env.rollout_buffers()
+    tail = rollout_tail(rewards_tn, terminated_tn)
     tail.update(
         logprobs=logprobs_tn[:steps].t().contiguous(),
         entropies=entropies_tn[:steps].t().contiguous(),

@@ -110,11 +110,16 @@ class GazeOracle:
         stop_enabled: bool = False,
         raster_masks: bool = False,
     ):
+        """``images`` may be a bare ``(B, C, H, W)`` shape instead of a tensor: the oracle then tracks every
+        integer / float output of the env but returns ``None`` for the crops -- full-size batches (1024 LARD
+        images are 74 GB as float32) are checked that way, with a sub-batch replayed with pixels."""
         bboxes = np.asarray(bboxes, dtype=np.int64)
-        assert images.shape[0] == bboxes.shape[0]
-        assert images.dim() == 4
+        self.has_pixels = isinstance(images, torch.Tensor)
+        shape = tuple(images.shape) if self.has_pixels else tuple(int(v) for v in images)
+        assert shape[0] == bboxes.shape[0]
+        assert len(shape) == 4
         assert n_glimps_levels == 1, "the oracle covers the single-level env only"
-        self.batch_size, self.n_channels, self.height, self.width = images.shape
+        self.batch_size, self.n_channels, self.height, self.width = shape
         assert self.height % patch_size == 0 and self.width % patch_size == 0
         self.patch_size, self.max_ep_len = patch_size, max_ep_len
         self.stop_enabled = stop_enabled
@@ -184,7 +189,9 @@ class GazeOracle:
             total = total + stop_eval.astype(np.float32)  # fp32 add #2
         return total.astype(np.float32)
 
-    def crops(self) -> torch.Tensor:  # general_env.py:285-306
+    def crops(self) -> Optional[torch.Tensor]:  # general_env.py:285-306
+        if not self.has_pixels:
+            return None
         p = self.patch_size
         tiles = [
             self.images[i, :, y * p : (y + 1) * p, x * p : (x + 1) * p]

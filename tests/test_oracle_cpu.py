@@ -125,6 +125,20 @@ def test_simple_env_oracle_matches_reference():
         assert sorted(env.bbox_patches) == [tuple(r) for r in c["bbox_patches"].tolist()]
 
 
+def test_simple_env_oracle_matches_reference_float_boxes():
+    """Boxes that are not whole pixels (the dataset's minimum-size resize, dataset.py:258-270): the reference keeps
+    python floats through the 5 % rule, the centre patch and the local boxes."""
+    fx = load_golden("simple_env_float.npz")
+    assert any((fx[f"{n}/raw_boxes"] != np.floor(fx[f"{n}/raw_boxes"])).any() for n in fx["names"])
+    for name in fx["names"]:
+        c, cfg = simple_case(fx, str(name))
+        env, s = run_traj_oracle(c, cfg)
+        for k in SAMPLE_KEYS:
+            assert s[k].dtype == torch.from_numpy(c[k]).dtype, (name, k)
+            assert np.array_equal(s[k].numpy(), c[k]), (name, k)
+        assert sorted(env.bbox_patches) == [tuple(r) for r in c["bbox_patches"].tolist()]
+
+
 def test_collate_oracle_matches_reference():
     fx = load_golden("simple_env.npz")
     samples = []

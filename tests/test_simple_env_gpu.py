@@ -41,6 +41,32 @@ def test_generate_sample_matches_reference_fixtures():
                 assert np.array_equal(s[k].cpu().numpy(), c[k]), (name, variant, k)
 
 
+def test_float_boxes_match_reference_fixtures():
+    """Boxes that are not whole pixels (dataset.py:258-270 scales them): labels, local boxes and detection boxes
+    come from the float64 coordinates (jn_patch_bitmaps_f64 / jn_local_boxes_f64), not from truncated ones --
+    per-env samples and the batched entry point, against samples of the unmodified reference."""
+    from jolineedle_b200.env.simple_env import NeedleSimpleEnv, generate_trajectories
+
+    fx = load_golden("simple_env_float.npz")
+    for name in fx["names"]:
+        c, cfg = simple_case(fx, str(name))
+        boxes = bboxes_of(c["raw_boxes"].tolist())
+        seed_python_random(cfg["seed"])
+        env = NeedleSimpleEnv(to_f32(c["u8"]).cuda(), cfg["P"], boxes, seed=cfg["seed"])
+        assert sorted(env.bbox_patches) == [tuple(r) for r in c["bbox_patches"].tolist()]
+        s = env.generate_sample(cfg["T"], cfg["kmin"], cfg["kmax"], binomial_keypoints=cfg["binomial"])
+        for k in SAMPLE_KEYS:
+            assert s[k].dtype == torch.from_numpy(c[k]).dtype, (name, k)
+            assert np.array_equal(s[k].cpu().numpy(), c[k]), (name, k)
+        seed_python_random(cfg["seed"])
+        got = generate_trajectories({"image": [torch.from_numpy(c["u8"]).cuda()], "bboxes": [boxes], "class_id": [0]},
+                                    cfg["P"], cfg["T"], cfg["kmin"], cfg["kmax"], binomial_keypoints=cfg["binomial"],
+                                    seeds=[cfg["seed"]], normalize=True, check=True)
+        for k in SAMPLE_KEYS:
+            want = c[k] if k in ("patches_yolox", "bboxes_yolox") else c[k][None]
+            assert np.array_equal(got[k].cpu().numpy(), want), (name, "batched", k)
+
+
 def test_collate_and_batched_entry_match_reference_fixtures():
     from jolineedle_b200.env.simple_env import NeedleSimpleEnv, generate_trajectories
 
