@@ -282,18 +282,26 @@ GatherTune gather_tune(int patch, int elem, bool plain_copy, bool focus, int eng
 template <typename Kernel>
 int persistent_ctas_per_sm(Kernel kernel, int threads, size_t smem, int device, int* per_sm) {
   struct Entry { const void* fn; size_t smem; int device, per_sm; };
+  struct Limit { const void* fn; int device; size_t smem; };  // largest dynamic size the function was opted into
   static std::mutex mu;
   static std::vector<Entry> cache;
+  static std::vector<Limit> limits;
   const void* fn = reinterpret_cast<const void*>(kernel);
-  {
-    std::lock_guard<std::mutex> lock(mu);
-    for (const auto& e : cache)
-      if (e.fn == fn && e.smem == smem && e.device == device) { *per_sm = e.per_sm; return JN_OK; }
+  std::lock_guard<std::mutex> lock(mu);
+  for (const auto& e : cache)
+    if (e.fn == fn && e.smem == smem && e.device == device) { *per_sm = e.per_sm; return JN_OK; }
+  // the opt-in limit is one value per function: only ever raise it, or a later launch at an earlier, larger
+  // size would be refused
+  Limit* lim = nullptr;
+  for (auto& l : limits)
+    if (l.fn == fn && l.device == device) lim = &l;
+  if (!lim) { limits.push_back({fn, device, 0}); lim = &limits.back(); }
+  if (smem > lim->smem) {
+    JN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lim->smem = smem;
   }
-  JN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int n = 0;
   JN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem));
-  std::lock_guard<std::mutex> lock(mu);
   cache.push_back({fn, smem, device, n});
   *per_sm = n;
   return JN_OK;
@@ -852,6 +860,10 @@ int gather_after(const jn_images* set, const jn_images* history_set, const jn_en
     GatherRequest rh;
     rh.src_index = p->history_src; rh.n_items = p->n; rh.out = p->out;
     rh.out_item_stride_bytes = p->out_item_stride_bytes; rh.flags = 0; rh.engine = p->engine; rh.status = p->status;
+    // behind the host gather with the programmatic attribute and WITHOUT a wait: that gather triggers its
+    // dependents right after it has itself waited for the step kernel, so this HBM -> HBM copy overlaps the
+    // PCIe-bound reads; the two write disjoint tiles of the slot
+    rh.pdl = true;
     if (int rc = gather_launch(history_set, rh, stream)) return rc;
   }
   return JN_OK;

@@ -150,6 +150,7 @@ gather_copy_kernel(const __grid_constant__ GatherArgs a, const __grid_constant__
   fence_proxy_async_smem();  // zeros (generic proxy) -> visible to the bulk stores (async proxy)
   __syncwarp();
   if (a.wait_prior) pdl_wait();  // everything above overlapped the tail of the kernel before us
+  pdl_launch_dependents();       // a gather launched behind this one (history reuse) may run next to it
 
   const int grid = gridDim.x;
   const int mine = a.total_chunks > (int)blockIdx.x ? (a.total_chunks - (int)blockIdx.x + grid - 1) / grid : 0;
@@ -449,6 +450,12 @@ gather_xform_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
   }
   __syncthreads();
   if (a.wait_prior) pdl_wait();  // barrier init / tensor-map prefetch overlapped the tail of the kernel before us
+  // A gather launched behind this one with the programmatic attribute may start now: in the zero-copy env that is
+  // the copy of revisited patches out of the crop history (HBM -> HBM), which then runs NEXT TO this PCIe-bound
+  // kernel instead of after it.  Everything it reads (history_src from the step kernel, older history slots) is
+  // complete by now: this kernel has just waited for the step kernel.  A normally launched successor still waits
+  // for this grid to finish.
+  pdl_launch_dependents();
 
   int st = 0;
   uint32_t phase = 0;  // parity of the ring round this warp is in
@@ -456,13 +463,14 @@ gather_xform_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
   if (warp == 0) {  // ---- TMA producer
     // Chunks are claimed from a global counter (a statically dealt grid drifts apart: SMs that see a faster
     // memory path finish early and leave a tail), in batches that shrink towards the end of the launch:
-    // up to 32 chunks (one per lane, decoded in parallel) early on, 4 at the end.
+    // up to 32 chunks (one per lane, decoded in parallel) early on, single chunks at the end (a 256-tile launch
+    // of the batched env lasts ~20 chunks per CTA: a tail of 4 was a tenth of it).
     const int total = a.total_chunks, grid = gridDim.x;
     auto claim = [&](int& base, int& size) {
       int b = 0, n = 0;
       if (lane == 0) {
         const int seen = *reinterpret_cast<volatile int*>(a.work_counter);
-        n = seen < total ? min(32, max(4, (total - seen) / (2 * grid))) : 1;
+        n = seen < total ? min(32, max(1, (total - seen) / (4 * grid))) : 1;
         b = atomicAdd(a.work_counter, n);
       }
       base = __shfl_sync(0xFFFFFFFFu, b, 0);

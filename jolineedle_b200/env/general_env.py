@@ -37,6 +37,23 @@ from ..gather import ImageSet
 from .common import Action, ACTION_DELTAS, DELTA_TABLE  # noqa: F401  (re-exported like the reference module)
 
 
+def _spaces(batch_size: int, channels: int, patch: int, rows: int, cols: int):
+    """``observation_space`` / ``action_space`` as the reference declares them (general_env.py:61-72): gymnasium
+    objects when that package is installed, plain descriptions with the same fields otherwise (no caller of the
+    reference reads them; the env does not depend on gymnasium)."""
+    shape = (batch_size, channels, patch, patch)
+    try:
+        import gymnasium as gym
+
+        return (gym.spaces.Box(low=0, high=1, shape=shape),
+                gym.spaces.Tuple((gym.spaces.Discrete(rows), gym.spaces.Discrete(cols))))
+    except Exception:
+        from types import SimpleNamespace
+
+        return (SimpleNamespace(low=0, high=1, shape=shape),
+                SimpleNamespace(spaces=(SimpleNamespace(n=rows), SimpleNamespace(n=cols))))
+
+
 class NeedleGeneralEnv:
     def __init__(
         self,
@@ -92,6 +109,8 @@ class NeedleGeneralEnv:
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self._normalize, self._focus, self._engine = normalize, focus, engine
+        self.observation_space, self.action_space = _spaces(self.batch_size, self.n_channels, patch_size,
+                                                            self.n_vertical_patches, self.n_horizontal_patches)
         self._shifts, self._shifts_aligned = None, False
         if translate is not None:
             t = torch.as_tensor(translate)

@@ -55,8 +55,9 @@ def boxes_array(bboxes: Sequence[Sequence], n_max: Optional[int] = None, want_fl
         return (arr, counts, n_max, True, None) if want_float else (arr, counts, n_max, True)
     # one conversion for the whole batch: BBox = ((y1, x1), (y2, x2)) -> flat list of 4 * total numbers
     # (flattening in python first is ~10x faster than letting numpy walk the nested tuples)
-    flat = np.array(list(_chain(_chain(_chain(bboxes)))))
-    exact = bool(np.issubdtype(flat.dtype, np.integer)) or bool(np.all(flat == np.floor(flat)))
+    # straight into a float64 buffer, no intermediate list (pixel coordinates are exact in float64)
+    flat = np.fromiter(_chain(_chain(_chain(bboxes))), dtype=np.float64, count=4 * total)
+    exact = bool(np.all(flat == np.floor(flat)))
     flat = flat.reshape(total, 4)[:, [1, 0, 3, 2]]  # -> x1, y1, x2, y2
     image = np.repeat(np.arange(n), counts)
     slot = np.arange(total) - np.repeat(np.cumsum(counts) - counts, counts)
@@ -115,11 +116,79 @@ _native_plan: Optional[_NativePlan] = None
 _det_capacity: Dict[tuple, int] = {}  # high-water mark of detection tiles per batch (see expand_packed)
 
 
+_native_verdict: Optional[bool] = None  # None = not checked yet in this process
+
+
+def native_planner_verified() -> bool:
+    """The native planner restates CPython's ``set`` / tuple hash / ``random`` and numpy's PCG64 streams; a new
+    interpreter or numpy release may change any of them.  On first use, a dozen seeded episodes are planned both
+    ways (the python planner calls the real objects); on any difference the native planner is switched off for
+    this process with a warning -- seeded trajectories then keep following the reference, just more slowly."""
+    global _native_verdict
+    if _native_verdict is not None:
+        return _native_verdict
+    import warnings
+
+    from .simple_env import NeedleSimpleEnv
+    from ..utils import BBox
+
+    class _Shape:
+        def __init__(self, h, w):
+            self.shape, self.is_cuda = (3, h, w), True
+
+    saved = random.getstate()
+    ok = True
+    try:
+        rng = np.random.default_rng(20240229)
+        for binomial in (False, True):
+            P = 16
+            grids = [(5, 6), (8, 9), (3, 3), (12, 7), (5, 6), (1, 4)]
+            bboxes = []
+            for gh, gw in grids:
+                raw = []
+                for _ in range(int(rng.integers(0, 4))):
+                    bw, bh = (int(v) for v in rng.integers(2, 3 * P, size=2))
+                    x1, y1 = int(rng.integers(-4, gw * P)), int(rng.integers(-4, gh * P))
+                    raw.append(BBox(Position(y1, x1), Position(y1 + bh, x1 + bw)))
+                bboxes.append(raw)
+            seeds = [int(v) for v in rng.integers(0, 2**62, size=len(grids))]
+            rows = np.array([g[0] for g in grids], dtype=np.int32)
+            cols = np.array([g[1] for g in grids], dtype=np.int32)
+            boxes, n_boxes, n_max, _ = boxes_array(bboxes)
+            random.seed(99)
+            a = plan_native(boxes, n_boxes, n_max, rows, cols, P, seeds, 0, 3, binomial, None)
+            state_native = random.getstate()
+            random.seed(99)
+            envs = [NeedleSimpleEnv(_Shape(gh * P, gw * P), P, bboxes[i], seeds[i]) for i, (gh, gw) in enumerate(grids)]
+            b = pack_python_plans(envs, [e.plan_sample(0, 3, binomial, None) for e in envs])
+            same = state_native == random.getstate() and all(
+                np.array_equal(getattr(a, k), getattr(b, k))
+                for k in ("start", "seg_begin", "seg_to", "seg_tgt", "seg_flags", "draw_begin", "draws", "det_begin",
+                          "det_yx"))
+            ok = ok and same
+    except Exception as exc:  # a planner that cannot even run is not trusted either
+        warnings.warn(f"jolineedle_b200: native planner self-check raised {exc!r}")
+        ok = False
+    finally:
+        random.setstate(saved)
+    if not ok:
+        warnings.warn("jolineedle_b200: the native planner no longer reproduces python's random / set / numpy "
+                      "streams on this interpreter (CPython or numpy changed?); falling back to the python planner")
+    _native_verdict = ok
+    return ok
+
+
 def native_supported(rows: np.ndarray, cols: np.ndarray, exact_boxes: bool, seeds) -> bool:
     if not exact_boxes or (len(rows) and (int(rows.max()) > 4096 or int(cols.max()) > 4096)):
         return False
-    if seeds is not None:
-        for s in seeds:
+    if seeds is not None and len(seeds):
+        try:  # one vectorised look at the common case: a list of non-negative python / numpy ints
+            arr = np.asarray(seeds)
+        except (OverflowError, ValueError):
+            arr = None
+        if arr is not None and arr.dtype.kind in "iu" and arr.ndim == 1:
+            return bool(arr.min() >= 0)
+        for s in seeds:  # mixed lists (None = unseeded episode), huge python ints
             if s is not None and not (isinstance(s, (int, np.integer)) and 0 <= int(s) < (1 << 64)):
                 return False
     return True
@@ -378,6 +447,10 @@ def plan_batch(bboxes: Sequence[Sequence], heights: Sequence[int], widths: Seque
     use_native = planner != "python" and native_supported(rows, cols, exact, seeds)
     if planner == "native" and not use_native:
         raise ValueError("the native planner needs integer boxes, grids up to 4096x4096 and seeds below 2**64")
+    if use_native and not native_planner_verified():
+        if planner == "native":
+            raise _cabi.NativeLibraryError("the native planner failed its self-check against the python planner")
+        use_native = False
     if use_native:
         ticket = plan_native_start(boxes, n_boxes, n_max, rows, cols, patch_size, seeds, min_keypoints, max_keypoints,
                                    binomial_keypoints, position)

@@ -69,6 +69,10 @@ class ImageSet:
         if len(devices) > 1 or any(t.dtype != dtype for t in slabs) or any(sh[-3] != channels for sh in shapes):
             raise ValueError("all images of a set must share device, dtype and channel count")
         cuda_device = torch.device("cuda", next(iter(devices))) if devices else None
+        for t, d in zip(slabs, where):
+            if d < 0 and not t.is_contiguous():
+                # .contiguous() of a pinned tensor is an ordinary pageable copy: its pointer means nothing to the GPU
+                raise ValueError("host-mapped (pinned) images must be contiguous; pin the contiguous copy instead")
         norm = [t if t.is_contiguous() else t.contiguous() for t in slabs]
         counts = [sh[0] if len(sh) == 4 else 1 for sh in shapes]
         heights, widths = [sh[-2] for sh in shapes], [sh[-1] for sh in shapes]
@@ -105,8 +109,13 @@ class ImageSet:
                 _cabi.dtype_code(dtype), self.patch_size, _cabi.ptr(self._table_host), _cabi.ptr(self._table),
                 _cabi.stream_ptr(self.device),
             )
+            self._table_ready, self._table_streams = None, set()
             if rc == _cabi.JN_OK and self._table is not None:
                 self._table.copy_(self._table_host, non_blocking=True)
+                # gathers on OTHER streams must not run before this copy: they wait for the event once each
+                self._table_ready = torch.cuda.Event()
+                self._table_ready.record()
+                self._table_streams.add(_cabi.stream_ptr(self.device))
         # same precondition as the reference envs: sizes must be multiples of the patch size
         _cabi.check(rc, invalid_exc=AssertionError)
         self._handle = handle
@@ -118,6 +127,15 @@ class ImageSet:
                 _cabi.lib().jn_images_destroy(h)
             except Exception:  # interpreter shutdown
                 pass
+
+    def _order_after_table(self):
+        """Multi-slab sets: the per-image table was uploaded on the stream that was current at construction; the
+        first gather on any other stream waits for that upload."""
+        if self._table_ready is not None:
+            sp = _cabi.stream_ptr(self.device)
+            if sp not in self._table_streams:
+                torch.cuda.current_stream(self.device).wait_event(self._table_ready)
+                self._table_streams.add(sp)
 
     def engine_available(self, engine: str) -> bool:
         return bool(_cabi.lib().jn_images_tma_ok(self._handle, _cabi.ENGINES[engine]))
@@ -147,6 +165,7 @@ class ImageSet:
         keep = (status, shifts, self)  # the raw pointers above stay valid as long as the closure lives
 
         def launch(positions: torch.Tensor, out: torch.Tensor):
+            self._order_after_table()
             n = positions.shape[0]
             stride = (out.stride(0) if n > 1 else out[0].numel()) * out.element_size()
             timing = TIMING
@@ -213,6 +232,7 @@ class ImageSet:
         if skip_negative:  # negative src_index: leave out[i] as it is (default: zero-fill it)
             flags |= _cabi.GATHER_SKIP_NEGATIVE
         stride = out.stride(0) * out.element_size() if n > 1 else out[0].numel() * out.element_size() if n else 0
+        self._order_after_table()
         timing = TIMING
         with _cabi.on_device(self.device):
             pair = timing.begin() if timing is not None else None

@@ -143,6 +143,35 @@ def test_out_of_grid_position_is_flagged_not_read():
         assert bool((out[1] == -1).all())  # skipped tile untouched
 
 
+def test_bad_image_index_on_a_list_of_images_is_flagged_not_dereferenced():
+    """src_index beyond the set: reported through the status word, the tile skipped -- on multi-slab sets the
+    per-image record of such an index must not be loaded at all (it lies outside the table)."""
+    from jolineedle_b200.gather import ImageSet
+
+    P = 16
+    imgs = [make_images(1, 2 * P, 3 * P, torch.float32, salt=i)[0] for i in range(3)]
+    s = ImageSet([t.cuda() for t in imgs], P)
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    pos = torch.tensor([[1, 2], [0, 0], [1, 1]], dtype=torch.int64, device="cuda")
+    src = torch.tensor([2, 1 << 20, 0], dtype=torch.int32, device="cuda")
+    for engine in ("bulk", "ldg", "auto"):
+        status.zero_()
+        out = torch.full((3, 3, P, P), -1.0, device="cuda")
+        s.gather(pos, src_index=src, out=out, engine=engine, status=status)
+        torch.cuda.synchronize()
+        assert int(status.item()) & 1, engine
+        assert torch.equal(out[0].cpu(), imgs[2][:, P:2 * P, 2 * P:3 * P])
+        assert bool((out[1] == -1).all()) and torch.equal(out[2].cpu(), imgs[0][:, P:2 * P, P:2 * P])
+
+
+def test_pinned_images_must_be_contiguous():
+    from jolineedle_b200.gather import ImageSet
+
+    host = torch.zeros((2, 3, 32, 64), dtype=torch.uint8).pin_memory()
+    with pytest.raises(ValueError):
+        ImageSet(host[:, :, :, ::2], 16, device="cuda")
+
+
 def test_size_mismatch_raises_like_the_reference():
     from jolineedle_b200.gather import ImageSet
 

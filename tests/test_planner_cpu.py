@@ -283,3 +283,45 @@ def test_native_planner_wide_grids_follow_numpy_btpe():
         _assert_same_plans(py, nat)
         segments += len(py.seg_flags)
     assert segments > 500
+
+
+def test_native_planner_self_check_and_fallback(monkeypatch):
+    """First use compares the native planner with the python one on seeded episodes; a mismatch (a CPython /
+    numpy bump) switches to the python planner with a warning instead of silently changing seeded trajectories."""
+    import warnings
+
+    from jolineedle_b200.env import trajectories as tr
+
+    monkeypatch.setattr(tr, "_native_verdict", None)
+    import random
+
+    random.seed(1234)
+    before = random.getstate()
+    assert tr.native_planner_verified() is True and tr._native_verdict is True
+    assert random.getstate() == before  # the check leaves python's global stream where it was
+
+    # a planner that disagrees: perturb one exported array
+    real = tr.plan_native
+
+    def broken(*a, **k):
+        p = real(*a, **k)
+        if len(p.seg_to):
+            p.seg_to = p.seg_to.copy()
+            p.seg_to[0, 0] += 1
+        return p
+
+    monkeypatch.setattr(tr, "_native_verdict", None)
+    monkeypatch.setattr(tr, "plan_native", broken)
+    with warnings.catch_warnings(record=True) as seen:
+        warnings.simplefilter("always")
+        assert tr.native_planner_verified() is False
+    assert any("falling back to the python planner" in str(w.message) for w in seen)
+    boxes = [[BBox(Position(10, 12), Position(60, 70))]]
+    random.seed(8)
+    a = tr.plan_batch(boxes, [128], [160], 32, 0, 3, True, None, [5], planner="auto")   # python planner now
+    monkeypatch.setattr(tr, "plan_native", real)
+    monkeypatch.setattr(tr, "_native_verdict", None)
+    random.seed(8)
+    b = tr.plan_batch(boxes, [128], [160], 32, 0, 3, True, None, [5], planner="native")
+    for k in ("start", "seg_begin", "seg_to", "seg_tgt", "seg_flags", "draw_begin", "draws", "det_begin", "det_yx"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k

@@ -1,48 +1,57 @@
 #!/bin/bash
-# One GPU session (run under gpurun from the repo root):
-#   smoke -> GPU parity suite -> bench lines (cfg 2 uint8 / fp32, cfg 3, cfg 4, reference arm)
-#   -> quick gather microbench.   Usage: bash tools/gpu_ci.sh [ncu]
-# With "ncu" it also captures the launch list and full profiles of the gather / step kernels, each
-# right after the same command has exited 0 without ncu (profiles/README.md says how they are read;
-# tools/ncu_summarize.py reduces the reports to profiles/r01/ncu_summary.json).
-mkdir -p gpurun_out
-rm -f gpurun_out/summary.txt
-note() { echo "$@" | tee -a gpurun_out/summary.txt; }
+# One GPU session (run under gpurun from the repo root).   Usage: bash tools/gpu_ci.sh <tag> [ncu] [micro]
+#   smoke -> GPU parity suite -> default bench line (cfg 3 + cfg 2 / cfg 4 nested) -> reference arm
+#   ncu:   launch lists + `--set full` captures of the gather / step kernels at the CONFIG batch sizes, each right
+#          after the same command has exited 0 without ncu (profiles/README.md says how they are read;
+#          tools/ncu_summarize.py reduces the reports to profiles/<round>/ncu_summary.json, stamped with the
+#          source hash written here)
+#   micro: cfg-5 microbenches (gather sweep quick, step kernel, fused step call)
+D=gpurun_out/${1:-ci}
+mkdir -p $D
+note() { echo "$@" | tee -a $D/summary.txt; }
+rm -f $D/summary.txt
+python -c "from jolineedle_b200 import buildinfo; print(buildinfo.library_source_hash())" > $D/source_hash.txt 2>&1
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv,noheader > $D/gpu.txt 2>&1
+{ nvidia-smi topo -m; lscpu | grep -iE "model name|socket|numa|^cpu\(s\)"; free -g | head -2; } > $D/topo.txt 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" > $D/smoke.log 2>&1; note "smoke rc=$?"
+timeout 2400 python -m pytest tests -m gpu -q --timeout 1200 > $D/pytest_gpu.log 2>&1
+note "pytest_gpu rc=$? $(tail -1 $D/pytest_gpu.log)"
+SECONDS=0
+timeout 1200 python bench.py --steps 20 --warmup 5 > $D/bench_default.json 2> $D/bench_default.err; note "bench default rc=$? (${SECONDS}s)"
+SECONDS=0
+timeout 900 python bench.py --impl reference --steps 20 --warmup 5 > $D/bench_reference.json 2> $D/bench_reference.err; note "bench reference rc=$? (${SECONDS}s)"
 
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv,noheader > gpurun_out/gpu.txt 2>&1
-{ nvidia-smi topo -m; lscpu | grep -iE "model name|socket|numa|^cpu\(s\)"; python -c "import os; print('affinity', sorted(os.sched_getaffinity(0)))"; free -g | head -2; } > gpurun_out/topo.txt 2>&1
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; note "smoke rc=$?"
-timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/pytest_gpu.log 2>&1
-note "pytest_gpu rc=$? $(tail -1 gpurun_out/pytest_gpu.log)"
-
-timeout 900 python bench.py > gpurun_out/bench_supervised.json 2> gpurun_out/bench_supervised.err; note "bench cfg2 u8 (default) rc=$?"
-timeout 900 python bench.py --src f32 > gpurun_out/bench_supervised_f32.json 2> gpurun_out/bench_supervised_f32.err; note "bench cfg2 f32 rc=$?"
-timeout 900 python bench.py --workload reinforce > gpurun_out/bench_reinforce.json 2> gpurun_out/bench_reinforce.err; note "bench cfg3 rc=$?"
-timeout 900 python bench.py --workload aerial > gpurun_out/bench_aerial.json 2> gpurun_out/bench_aerial.err; note "bench cfg4 rc=$?"
-timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; note "bench reference rc=$?"
-rm -f gpurun_out/micro_quick.jsonl gpurun_out/micro_translate.jsonl
-timeout 600 python tools/microbench_gather.py --quick --engines tensor,bulk,auto --out gpurun_out/micro_quick.jsonl > gpurun_out/micro_quick.log 2>&1; note "micro rc=$?"
-timeout 600 python tools/microbench_gather.py --quick --batches 2048 --translate --engines auto,ldg --out gpurun_out/micro_translate.jsonl > gpurun_out/micro_translate.log 2>&1; note "micro translate rc=$?"
-
-if [ "$1" = "ncu" ]; then
-  CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
-  $CMD > gpurun_out/plain_sup.log 2>&1 &&
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_sup.csv $CMD > gpurun_out/ncu_launches_sup.log 2>&1
-  note "ncu launches rc=$?"
-  $CMD > gpurun_out/plain_sup2.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:"gather_xform|traj_expand" -s 6 -c 3 -o gpurun_out/prof_sup_u8 $CMD > gpurun_out/ncu_sup.log 2>&1
-  note "ncu supervised u8 rc=$?"
-  CMD="python bench.py --src f32 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
-  $CMD > gpurun_out/plain_sup_f32.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:"gather_copy" -s 6 -c 2 -o gpurun_out/prof_sup_f32 $CMD > gpurun_out/ncu_sup_f32.log 2>&1
-  note "ncu supervised f32 rc=$?"
-  CMD="python bench.py --workload reinforce --steps 1 --warmup 3 --batch 256 --no-e2e --no-cpu-baseline"
-  $CMD > gpurun_out/plain_rl.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:"env_step|gather_xform" -s 130 -c 4 -o gpurun_out/prof_rl $CMD > gpurun_out/ncu_rl.log 2>&1
-  note "ncu reinforce rc=$?"
-  CMD="python bench.py --workload aerial --steps 1 --warmup 3 --batch 64 --no-e2e --no-cpu-baseline"
-  $CMD > gpurun_out/plain_aerial.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:"env_step|gather_xform" -s 200 -c 4 -o gpurun_out/prof_aerial $CMD > gpurun_out/ncu_aerial.log 2>&1
-  note "ncu aerial rc=$?"
+for arg in "$@"; do
+if [ "$arg" = "micro" ]; then
+  rm -f $D/micro_step.jsonl $D/micro_fused.jsonl $D/micro_quick.jsonl $D/micro_translate.jsonl
+  timeout 600 python tools/microbench_step.py --out $D/micro_step.jsonl > $D/micro_step.log 2>&1; note "micro step rc=$?"
+  timeout 900 python tools/microbench_step.py --fused --out $D/micro_fused.jsonl > $D/micro_fused.log 2>&1; note "micro fused rc=$?"
+  timeout 600 python tools/microbench_gather.py --quick --engines auto --out $D/micro_quick.jsonl > $D/micro_quick.log 2>&1; note "micro gather rc=$?"
+  timeout 600 python tools/microbench_gather.py --patches 128,256 --batches 64,256,512 --modes u8 --engines auto --out $D/micro_small.jsonl > $D/micro_small.log 2>&1; note "micro small rc=$?"
+  timeout 600 python tools/microbench_gather.py --patches 256 --batches 256,2048 --modes u8 --translate --engines auto --out $D/micro_translate.jsonl > $D/micro_translate.log 2>&1; note "micro translate rc=$?"
 fi
-cat gpurun_out/summary.txt
+if [ "$arg" = "ncu" ]; then
+  CMD="python bench.py --steps 2 --warmup 3 --also none --no-e2e --no-cpu-baseline"
+  $CMD > $D/plain_rl.log 2>&1 &&
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $D/launches_reinforce.csv $CMD > $D/ncu_launches_rl.log 2>&1
+  note "ncu launches cfg3 rc=$?"
+  $CMD > $D/plain_rl2.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:"env_step|gather_xform" -s 130 -c 4 -o $D/prof_reinforce $CMD > $D/ncu_rl.log 2>&1
+  note "ncu cfg3 (B=1024) rc=$?"
+  CMD="python bench.py --workload aerial --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
+  $CMD > $D/plain_aerial.log 2>&1 &&
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file $D/launches_aerial.csv $CMD > $D/ncu_launches_aerial.log 2>&1
+  note "ncu launches cfg4 rc=$?"
+  $CMD > $D/plain_aerial2.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:"env_step|gather_xform" -s 200 -c 4 -o $D/prof_aerial $CMD > $D/ncu_aerial.log 2>&1
+  note "ncu cfg4 (B=256) rc=$?"
+  CMD="python bench.py --workload supervised --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
+  $CMD > $D/plain_sup.log 2>&1 &&
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $D/launches_supervised.csv $CMD > $D/ncu_launches_sup.log 2>&1
+  note "ncu launches cfg2 rc=$?"
+  $CMD > $D/plain_sup2.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:"gather_xform|traj_expand" -s 6 -c 3 -o $D/prof_supervised $CMD > $D/ncu_sup.log 2>&1
+  note "ncu cfg2 rc=$?"
+fi
+done
+cat $D/summary.txt

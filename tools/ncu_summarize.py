@@ -28,6 +28,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("reports", nargs="+", help="NAME=path.ncu-rep")
     ap.add_argument("--out", required=True)
+    ap.add_argument("--source-hash", default=None,
+                    help="digest of the native sources the profiled library was built from (jn_source_hash(), written "
+                         "by tools/gpu_ci.sh next to the reports); bench.py quotes a capture only for matching code")
+    ap.add_argument("--note", default=None, help="the profiled command, recorded next to the hash")
     args = ap.parse_args()
     summary = {}
     if os.path.exists(args.out):
@@ -63,9 +67,13 @@ def main():
                 "block": row[col["Block Size"]] if "Block Size" in col else None,
             })
         summary[name] = kernels
+        if args.source_hash:
+            summary.setdefault("_meta", {})[name] = {"source_hash": args.source_hash.strip(), "command": args.note}
     with open(args.out, "w") as f:
         json.dump(summary, f, indent=1)
     for name, kernels in summary.items():
+        if name == "_meta":
+            continue
         for k, recs in kernels.items():
             for r in recs:
                 t = r["dram_traffic_bytes"]
