@@ -117,7 +117,8 @@ cudaError_t launch_kernel(void (*kernel)(Params...), dim3 grid, dim3 block, size
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute attr[1];
-  if (pdl) {
+  static const bool pdl_enabled = [] { const char* e = getenv("JN_PDL"); return !(e && e[0] == '0'); }();  // A/B knob
+  if (pdl && pdl_enabled) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
@@ -307,15 +308,52 @@ int persistent_ctas_per_sm(Kernel kernel, int threads, size_t smem, int device, 
   return JN_OK;
 }
 
+// Ticket schedule of the converting gather (gather_xform_kernel): which chunks a ticket stands for.  The
+// producer claims tickets three batches ahead (that is what hides the decode latency), so a CTA that falls
+// behind still owns three batches when the tickets run out: batches are therefore SMALL -- 4 chunks for the bulk
+// of the launch, then per CTA three batches of 2 and six single chunks -- so that what a slow CTA still holds
+// (<= 12 chunks) is about what every other CTA draws from the fine-grained end (12 chunks).  (Batches of 32, one
+// chunk per producer lane, with the same look-ahead left a slow CTA 96 chunks behind: -5 % on cfg 3.)  A launch
+// too short for all of it drops the large sizes first.  Segments are stored in launch order.
+void claim_schedule(jnk::GatherArgs& a, int grid) {
+  constexpr int kHead = 4, kTail = 2;
+  static const int sizes[kTail] = {1, 2}, per_cta[kTail] = {6, 3};
+  int rem = a.total_chunks, counts[kTail] = {0, 0};
+  for (int j = 0; j < kTail && rem > 0; ++j) {
+    long long want = (long long)per_cta[j] * grid;  // batches
+    const bool all = want * sizes[j] <= rem;
+    if (!all) want = rem / sizes[j];
+    counts[j] = (int)want;
+    rem -= (int)want * sizes[j];
+    if (!all) break;  // out of work: what is left (< sizes[j] chunks) opens the launch
+  }
+  int n = 0, ticket = 0, chunk = 0;
+  auto push = [&](int size, int batches, int chunks) {
+    if (batches <= 0) return;
+    a.sched_size[n] = size; a.sched_ticket[n] = ticket; a.sched_chunk[n] = chunk;
+    ticket += batches; chunk += chunks; ++n;
+  };
+  push(kHead, (rem + kHead - 1) / kHead, rem);  // head, the last batch possibly partial
+  for (int j = kTail - 1; j >= 0; --j) push(sizes[j], counts[j], counts[j] * sizes[j]);
+  a.sched_n = n;
+  for (int j = n; j < 7; ++j) { a.sched_ticket[j] = ticket; a.sched_chunk[j] = chunk; }
+  for (int j = n; j < 6; ++j) a.sched_size[j] = 1;
+}
+
 template <typename Kernel, typename... Extra>
-int launch_persistent(Kernel kernel, const jnk::GatherArgs& a, const CUtensorMap& map, int threads, size_t smem,
+int launch_persistent(Kernel kernel, const jnk::GatherArgs& args, const CUtensorMap& map, int threads, size_t smem,
                       const DeviceInfo& dev, cudaStream_t stream, int ctas_cap, bool pdl, Extra... extra) {
   int per_sm = 0;
   if (int rc = persistent_ctas_per_sm(kernel, threads, smem, dev.device, &per_sm)) return rc;
   if (per_sm < 1) return fail(JN_ERR_CUDA, "gather kernel does not fit on an SM (%zu bytes of shared memory)", smem);
   if (ctas_cap > 0 && per_sm > ctas_cap) per_sm = ctas_cap;
   long long grid = (long long)dev.sm_count * per_sm;
-  if (grid > a.total_chunks) grid = a.total_chunks;
+  if (grid > args.total_chunks) grid = args.total_chunks;
+  jnk::GatherArgs a = args;
+  if (a.work_counter) {
+    claim_schedule(a, (int)grid);
+    if (a.sched_ticket[a.sched_n] < grid) grid = a.sched_ticket[a.sched_n];  // never more CTAs than tickets
+  }
   JN_CUDA(launch_kernel(kernel, dim3((unsigned)grid), dim3((unsigned)threads), smem, stream, pdl, a, map, extra...));
   return JN_OK;
 }
@@ -664,6 +702,19 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
 }
 
 long long jn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// Host-only view of the converting gather's ticket schedule (tests: the tickets must tile [0, total) exactly).
+int jn_claim_schedule_host(int total_chunks, int grid, int32_t* sizes /*[6]*/, int32_t* tickets /*[7]*/,
+                           int32_t* chunks /*[7]*/) {
+  JN_REQUIRE(total_chunks >= 1 && grid >= 1 && sizes && tickets && chunks, "jn_claim_schedule_host: bad arguments");
+  jnk::GatherArgs a;
+  memset(&a, 0, sizeof(a));
+  a.total_chunks = total_chunks;
+  claim_schedule(a, grid);
+  for (int j = 0; j < 6; ++j) sizes[j] = a.sched_size[j];
+  for (int j = 0; j < 7; ++j) { tickets[j] = a.sched_ticket[j]; chunks[j] = a.sched_chunk[j]; }
+  return a.sched_n;
+}
 
 #ifndef JN_SOURCE_HASH
 #define JN_SOURCE_HASH "unknown"

@@ -50,7 +50,12 @@ struct GatherArgs {
   int box_w, kbox;              // tensor engine: patch = box_w * kbox
   int pitch, stage_bytes;       // xform kernel: bytes per staged row (patch * elem, + 16 when translating), per stage
   uint32_t wpr_magic;           // xform kernel: ceil(2^32 / (patch / 4)), division by multiply-high
-  int* work_counter;            // xform kernel: {next unclaimed chunk, CTAs done}; zero before and after a launch
+  int* work_counter;            // xform kernel: {next ticket, CTAs done}; zero before and after a launch
+  // xform kernel: the ticket schedule (see claim_schedule in jn_api.cu).  Ticket k of segment j
+  // (sched_ticket[j] <= k < sched_ticket[j+1]) is the batch of up to sched_size[j] chunks starting at
+  // sched_chunk[j] + (k - sched_ticket[j]) * sched_size[j], cut at sched_chunk[j+1].
+  int sched_n;
+  int sched_size[6], sched_ticket[7], sched_chunk[7];
   int padded;                   // image sizes are rounded up to the patch grid, pixels outside the image are zeros
   int skip_negative;            // negative src_index: 1 = leave the output tile untouched, 0 = zero-fill it
   // fused env step (jn_env_step_gather): `positions` are the positions BEFORE the move and the kernel applies
@@ -365,19 +370,49 @@ struct ChunkPlan {
   int cx, cy, plane;            // tensor-map coordinates
 };
 
-// Image index of chunk q's item (first half of the decode: the only load the second half depends on).
-__device__ __forceinline__ int chunk_image(const GatherArgs& a, int q, bool valid) {
+// The decode of a chunk needs three dependent memory round trips (claim -> src_index -> position / action /
+// shift / image record).  The producer takes them one batch apart (see gather_xform_kernel), so the decode is
+// split where the dependencies are: each function only ISSUES loads whose addresses it can already compute and
+// hands the raw registers on; nothing looks at a loaded value before the next stage, one batch later.
+
+// Stage B: image index of chunk q's item.
+__device__ __forceinline__ int load_chunk_image(const GatherArgs& a, int q, bool valid) {
   if (!valid) return -1;
   const int item = q / (a.channels * a.chunks_per_plane);
   return a.src_index ? a.src_index[item] : item;
 }
 
-// Second half of the decode, given the image index: position and image record (independent loads).
+// Stage C: everything else the plan of a chunk reads from memory.
+struct ChunkLoads {
+  int q, img;           // chunk (negative: lane idle) and image index
+  long long y, x, act;  // patch position and action code as stored
+  int sy, sx;           // translation of the image
+  ImageRec rec;         // multi-slab sets: the image's record
+};
+
+__device__ __forceinline__ ChunkLoads load_chunk_inputs(const GatherArgs& a, int q, bool valid, int img) {
+  ChunkLoads c;
+  c.q = valid ? q : -1; c.img = img;
+  c.y = c.x = 0; c.act = kStop; c.sy = c.sx = 0;
+  c.rec.base = nullptr; c.rec.height = c.rec.width = c.rec.slab = c.rec.plane0 = 0;
+  if (!valid || img < 0) return c;
+  const long long item = q / (a.channels * a.chunks_per_plane);
+  if (a.positions) { c.y = a.positions[2 * item]; c.x = a.positions[2 * item + 1]; }
+  if (a.actions) c.act = a.actions[item];
+  if (img < a.n_images) {  // (a bad index is reported by plan_chunk, never dereferenced)
+    if (a.shifts) { c.sy = a.shifts[2 * img]; c.sx = a.shifts[2 * img + 1]; }
+    if (a.images) c.rec = a.images[img];
+  }
+  return c;
+}
+
+// Stage D: pure arithmetic on the loaded values -> what the TMA issue needs.
 template <bool kShift>
-__device__ __forceinline__ ChunkPlan plan_chunk(const GatherArgs& a, int q, bool valid, int img) {
+__device__ __forceinline__ ChunkPlan plan_chunk(const GatherArgs& a, const ChunkLoads& c) {
   ChunkPlan p;
   p.dst = p.src = 0; p.src_row_bytes = 0; p.chrow = 0; p.flags = kDescSkip; p.cx = p.cy = p.plane = 0;
-  if (!valid) return p;
+  if (c.q < 0) return p;
+  const int q = c.q, img = c.img;
   const int cpi = a.channels * a.chunks_per_plane;
   const int item = q / cpi;
   const int rem = q - item * cpi;
@@ -389,14 +424,18 @@ __device__ __forceinline__ ChunkPlan plan_chunk(const GatherArgs& a, int q, bool
     p.flags = (a.skip_negative || img < -1) ? kDescSkip : kDescZero;
     return p;
   }
-  long long y, x;
-  item_position(a, item, y, x);
+  long long y = c.y, x = c.x;
+  if (a.actions) {  // fused env step: same move + clamp as env_step_kernel (see item_position)
+    long long act = c.act;
+    if (act < 0 || act > kStop) act = kStop;
+    y = lmin(lmax(y + kActionDy[act], 0), a.grid_rows - 1);
+    x = lmin(lmax(x + kActionDx[act], 0), a.grid_cols - 1);
+  }
   const uint8_t* base;
   int h, w;
   if (a.images) {
-    const ImageRec r = a.images[img < a.n_images ? img : 0];
-    base = r.base; h = r.height; w = r.width;
-    p.plane = r.plane0 + channel;
+    base = c.rec.base; h = c.rec.height; w = c.rec.width;
+    p.plane = c.rec.plane0 + channel;
   } else {
     base = a.base + (long long)img * a.image_stride; h = a.height; w = a.width;
     p.plane = img * a.channels + channel;
@@ -408,7 +447,7 @@ __device__ __forceinline__ ChunkPlan plan_chunk(const GatherArgs& a, int q, bool
   }
   p.flags = 0;
   const int px = (int)x, py = (int)y;
-  const int sy = a.shifts ? a.shifts[2 * img] : 0, sx = a.shifts ? a.shifts[2 * img + 1] : 0;
+  const int sy = c.sy, sx = c.sx;
   p.src_row_bytes = w * a.elem;
   p.src = reinterpret_cast<unsigned long long>(base + (((long long)channel * h + y * a.patch + row0) * w + x * a.patch) * a.elem);
   if (kShift) {
@@ -461,36 +500,54 @@ gather_xform_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
   uint32_t phase = 0;  // parity of the ring round this warp is in
 
   if (warp == 0) {  // ---- TMA producer
-    // Chunks are claimed from a global counter (a statically dealt grid drifts apart: SMs that see a faster
-    // memory path finish early and leave a tail), in batches that shrink towards the end of the launch:
-    // up to 32 chunks (one per lane, decoded in parallel) early on, single chunks at the end (a 256-tile launch
-    // of the batched env lasts ~20 chunks per CTA: a tail of 4 was a tenth of it).
+    // Work is handed out as TICKETS from a global counter (a statically dealt grid drifts apart: SMs that see
+    // a faster memory path finish early and leave a tail).  Ticket k stands for a small batch of chunks fixed
+    // by a schedule the host computed for this launch (claim_schedule in jn_api.cu: 4 chunks, then 2, then
+    // single chunks at the end).  The sizes depend on the ticket number only, not on how much work seemed to be
+    // left when it was drawn -- tickets are drawn three batches ahead (below), when that estimate would be stale.
+    //
+    // Decoding a batch takes three dependent round trips to memory (ticket, src_index, positions & co): ~3 us,
+    // as long as 3-4 chunks take to convert.  They run as a software pipeline, one batch apart, so that the
+    // warp never looks at a value in the iteration that asked for it:
+    //     A  atomicAdd for the ticket of batch b+3      (result read in the next iteration)
+    //     B  src_index loads of batch b+2               (   "    )
+    //     C  position / action / shift / record loads of batch b+1
+    //     D  arithmetic + TMA issue of batch b
+    // The first ticket of every CTA is its own index (no round trip before the first load); the counter hands
+    // out the tickets from gridDim.x on.  Claims still in flight when the tickets run out are harmless.
     const int total = a.total_chunks, grid = gridDim.x;
-    auto claim = [&](int& base, int& size) {
-      int b = 0, n = 0;
-      if (lane == 0) {
-        const int seen = *reinterpret_cast<volatile int*>(a.work_counter);
-        n = seen < total ? min(32, max(1, (total - seen) / (4 * grid))) : 1;
-        b = atomicAdd(a.work_counter, n);
-      }
-      base = __shfl_sync(0xFFFFFFFFu, b, 0);
-      size = __shfl_sync(0xFFFFFFFFu, n, 0);
+    auto ticket_range = [&](int k, int& base, int& size) {
+      base = total; size = 0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        if (j < a.sched_n && k >= a.sched_ticket[j] && k < a.sched_ticket[j + 1]) {
+          base = a.sched_chunk[j] + (k - a.sched_ticket[j]) * a.sched_size[j];
+          size = min(a.sched_size[j], a.sched_chunk[j + 1] - base);
+        }
     };
-    auto plan = [&](int base, int size) {
-      const int q = base + lane;
-      const bool valid = lane < size && q < total;
-      return plan_chunk<kShift>(a, q, valid, chunk_image(a, q, valid));
-    };
-    // software pipeline: while batch b is issued, the loads that decode batch b+1 are in flight
-    int base, size;
-    claim(base, size);
-    ChunkPlan cur = plan(base, size);
+    auto claim = [&]() { return lane == 0 ? atomicAdd(a.work_counter, 1) : 0; };
+    // A: ticket of batch 1
+    int a_ret = claim();
+    // B: batch 0
+    int b_base, b_size;
+    ticket_range((int)blockIdx.x, b_base, b_size);
+    int b_img = load_chunk_image(a, b_base + lane, lane < b_size);
+    // C: batch 0 (waits for B once); B: batch 1 (waits for A once); A: batch 2
+    int c_base = b_base, c_size = b_size;
+    ChunkLoads c = load_chunk_inputs(a, c_base + lane, lane < c_size, b_img);
+    ticket_range(grid + __shfl_sync(0xFFFFFFFFu, a_ret, 0), b_base, b_size);
+    b_img = load_chunk_image(a, b_base + lane, lane < b_size);
+    a_ret = claim();
     bool ring_used = false;  // true once every stage has been filled once
-    while (base < total) {
-      int next_base, next_size;
-      claim(next_base, next_size);
-      const ChunkPlan nxt = plan(next_base, next_size);
-      const int count = min(size, total - base);
+    while (c_base < total) {
+      const ChunkPlan cur = plan_chunk<kShift>(a, c);  // D: the loads of C were issued one batch ago
+      const int count = c_size;
+      // advance the pipeline before issuing, so that its loads fly while the ring is being fed
+      c_base = b_base; c_size = b_size;
+      c = load_chunk_inputs(a, c_base + lane, lane < c_size, b_img);
+      ticket_range(grid + __shfl_sync(0xFFFFFFFFu, a_ret, 0), b_base, b_size);
+      b_img = load_chunk_image(a, b_base + lane, lane < b_size);
+      a_ret = claim();
       for (int k = 0; k < count; ++k) {
         const int flags = __shfl_sync(0xFFFFFFFFu, cur.flags, k);
         const int chrow = __shfl_sync(0xFFFFFFFFu, cur.chrow, k);
@@ -524,8 +581,11 @@ gather_xform_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
         }
         if (++st == stages) { st = 0; phase ^= 1u; ring_used = true; }
       }
-      cur = nxt; base = next_base; size = next_size;
     }
+    // the claim that is still in flight has to land before this CTA reports itself done: whoever resets the
+    // counters for the next launch must be the last one to touch them
+    asm volatile("" ::"r"(a_ret), "r"(b_img) : "memory");
+    __threadfence();
     // tell the consumers to leave, then clean the counters up for the next launch: the last CTA whose claims
     // have all come back empty knows that nobody will touch them again
     if (ring_used) mbar_wait(&empty[st], phase ^ 1u);

@@ -136,36 +136,40 @@ def native_planner_verified() -> bool:
         def __init__(self, h, w):
             self.shape, self.is_cuda = (3, h, w), True
 
+    import contextlib
+    import io
+
     saved = random.getstate()
     ok = True
     try:
-        rng = np.random.default_rng(20240229)
-        for binomial in (False, True):
-            P = 16
-            grids = [(5, 6), (8, 9), (3, 3), (12, 7), (5, 6), (1, 4)]
-            bboxes = []
-            for gh, gw in grids:
-                raw = []
-                for _ in range(int(rng.integers(0, 4))):
-                    bw, bh = (int(v) for v in rng.integers(2, 3 * P, size=2))
-                    x1, y1 = int(rng.integers(-4, gw * P)), int(rng.integers(-4, gh * P))
-                    raw.append(BBox(Position(y1, x1), Position(y1 + bh, x1 + bw)))
-                bboxes.append(raw)
-            seeds = [int(v) for v in rng.integers(0, 2**62, size=len(grids))]
-            rows = np.array([g[0] for g in grids], dtype=np.int32)
-            cols = np.array([g[1] for g in grids], dtype=np.int32)
-            boxes, n_boxes, n_max, _ = boxes_array(bboxes)
-            random.seed(99)
-            a = plan_native(boxes, n_boxes, n_max, rows, cols, P, seeds, 0, 3, binomial, None)
-            state_native = random.getstate()
-            random.seed(99)
-            envs = [NeedleSimpleEnv(_Shape(gh * P, gw * P), P, bboxes[i], seeds[i]) for i, (gh, gw) in enumerate(grids)]
-            b = pack_python_plans(envs, [e.plan_sample(0, 3, binomial, None) for e in envs])
-            same = state_native == random.getstate() and all(
-                np.array_equal(getattr(a, k), getattr(b, k))
-                for k in ("start", "seg_begin", "seg_to", "seg_tgt", "seg_flags", "draw_begin", "draws", "det_begin",
-                          "det_yx"))
-            ok = ok and same
+      with contextlib.redirect_stdout(io.StringIO()):  # the python planner prints the reference's warnings
+          rng = np.random.default_rng(20240229)
+          for binomial in (False, True):
+              P = 16
+              grids = [(5, 6), (8, 9), (3, 3), (12, 7), (5, 6), (1, 4)]
+              bboxes = []
+              for gh, gw in grids:
+                  raw = []
+                  for _ in range(int(rng.integers(0, 4))):
+                      bw, bh = (int(v) for v in rng.integers(2, 3 * P, size=2))
+                      x1, y1 = int(rng.integers(-4, gw * P)), int(rng.integers(-4, gh * P))
+                      raw.append(BBox(Position(y1, x1), Position(y1 + bh, x1 + bw)))
+                  bboxes.append(raw)
+              seeds = [int(v) for v in rng.integers(0, 2**62, size=len(grids))]
+              rows = np.array([g[0] for g in grids], dtype=np.int32)
+              cols = np.array([g[1] for g in grids], dtype=np.int32)
+              boxes, n_boxes, n_max, _ = boxes_array(bboxes)
+              random.seed(99)
+              a = plan_native(boxes, n_boxes, n_max, rows, cols, P, seeds, 0, 3, binomial, None)
+              state_native = random.getstate()
+              random.seed(99)
+              envs = [NeedleSimpleEnv(_Shape(gh * P, gw * P), P, bboxes[i], seeds[i]) for i, (gh, gw) in enumerate(grids)]
+              b = pack_python_plans(envs, [e.plan_sample(0, 3, binomial, None) for e in envs])
+              same = state_native == random.getstate() and all(
+                  np.array_equal(getattr(a, k), getattr(b, k))
+                  for k in ("start", "seg_begin", "seg_to", "seg_tgt", "seg_flags", "draw_begin", "draws", "det_begin",
+                            "det_yx"))
+              ok = ok and same
     except Exception as exc:  # a planner that cannot even run is not trusted either
         warnings.warn(f"jolineedle_b200: native planner self-check raised {exc!r}")
         ok = False

@@ -41,6 +41,33 @@ def test_host_selftest_matches_torch_and_reference_table():
     assert list(direction) == [4, 2, 5, 0, 8, 1, 6, 3, 7]
 
 
+def test_gather_ticket_schedule_tiles_the_launch():
+    """The converting gather hands its chunks out as tickets; whatever the launch size and grid, the tickets must
+    cover every chunk exactly once, in order, with batch sizes that never grow towards the end."""
+    lib = _cabi.lib()
+    rng = np.random.default_rng(0)
+    cases = [(1, 1), (3, 3), (6144, 296), (43008, 148), (49152, 296), (31, 148), (296, 296), (297, 296), (1 << 20, 444)]
+    cases += [(int(rng.integers(1, 200000)), int(rng.integers(1, 600))) for _ in range(200)]
+    for total, grid in cases:
+        grid = min(grid, total)
+        sizes, tickets, chunks = (ctypes.c_int32 * 6)(), (ctypes.c_int32 * 7)(), (ctypes.c_int32 * 7)()
+        n = lib.jn_claim_schedule_host(total, grid, sizes, tickets, chunks)
+        assert 1 <= n <= 6 and tickets[0] == 0 and chunks[0] == 0 and chunks[n] == total, (total, grid)
+        covered, last_size = 0, 33
+        for j in range(n):
+            n_batches = tickets[j + 1] - tickets[j]
+            assert n_batches > 0 and 1 <= sizes[j] <= 4 and sizes[j] < last_size
+            last_size = sizes[j]
+            span = chunks[j + 1] - chunks[j]
+            assert (n_batches - 1) * sizes[j] < span <= n_batches * sizes[j]  # only the last batch may be partial
+            assert chunks[j] == covered
+            covered += span
+        assert covered == total
+        # the tail is fine-grained: a CTA never holds more than a few chunks when the tickets run out
+        if total >= 12 * grid:
+            assert sizes[n - 1] == 1 and tickets[n] - tickets[n - 1] == 6 * grid
+
+
 def test_invalid_arguments_are_reported_not_crashed():
     lib = _cabi.lib()
     handle = ctypes.c_void_p()

@@ -91,11 +91,19 @@ def test_reference_rollout_source_runs_on_the_drop_in(do_detection, stop_enabled
     ref, det_ref = results["reference"]
     got, det_got = results["ours"]
     assert set(ref) == set(got)
-    for k in ("rewards", "returns", "masks", "logit_masks", "positions", "patches", "prop_patches_found", "terminated"):
+    for k in ("rewards", "masks", "logit_masks", "positions", "patches", "prop_patches_found", "terminated"):
         assert ref[k].dtype == got[k].dtype and tuple(ref[k].shape) == tuple(got[k].shape), k
         assert torch.equal(ref[k], got[k].cpu()), k
-    for k in ("logprobs", "entropies"):  # policy-side float math: CPU vs GPU libm
+    # trainer-side float math (the reference's own torch.cumsum / Categorical, here on CUDA instead of the CPU):
+    # within the 1e-6 the north star allows for returns
+    for k in ("returns", "logprobs", "entropies"):
+        assert tuple(ref[k].shape) == tuple(got[k].shape), k
         assert torch.allclose(ref[k], got[k].cpu(), rtol=1e-5, atol=1e-6), k
+    # ... while the package's own returns tail (K3, on the env's step-major rings) reproduces the CPU cumsum bit for bit
+    from jolineedle_b200.reinforce import rollout_tail
+
+    r_tn, t_tn, _ = env.rollout_buffers()
+    assert torch.equal(rollout_tail(r_tn, t_tn)["returns"].cpu(), ref["returns"])
     assert ref["bboxes"] == got["bboxes"] and det_ref.seen == det_got.seen  # detector saw the same crops
     assert len(ref["bboxes"][0]) == ((ref["rewards"].shape[1] + 1) if do_detection else 0)
 
