@@ -153,10 +153,10 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
               uint32_t flags, int engine /*jn_engine*/, int32_t* status, void* stream);
 
 /* Host-only: the ticket schedule the converting gather uses for a launch of `total_chunks` chunks on `grid`
- * CTAs (work is claimed from a global counter in batches of 4 chunks, shrinking to single chunks at the end of
- * the launch).  Returns the number of segments n (<= 6); segment j hands out tickets [tickets[j], tickets[j+1])
+ * CTAs (work is claimed from a global counter in batches of `batch` chunks -- a power of two <= 32 -- shrinking
+ * to single chunks at the end of the launch).  Returns the number of segments n (<= 6); segment j hands out tickets [tickets[j], tickets[j+1])
  * as batches of sizes[j] chunks starting at chunks[j].  For tests: the tickets tile [0, total_chunks). */
-int jn_claim_schedule_host(int total_chunks, int grid, int32_t* sizes /*HOST [6]*/,
+int jn_claim_schedule_host(int total_chunks, int grid, int batch, int32_t* sizes /*HOST [6]*/,
                            int32_t* tickets /*HOST [7]*/, int32_t* chunks /*HOST [7]*/);
 
 /* ------------------------------------------------------------------------------------------

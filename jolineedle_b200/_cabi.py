@@ -52,7 +52,7 @@ SIGNATURES = {
     "jn_last_error": (c_char_p, []),
     "jn_launch_count": (c_longlong, []),
     "jn_source_hash": (c_char_p, []),
-    "jn_claim_schedule_host": (c_int, [c_int, c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
+    "jn_claim_schedule_host": (c_int, [c_int, c_int, c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
     "jn_env_step_gather": (c_int, [_P, _P, POINTER(EnvStepArgs), _P]),
     "jn_env_reset_gather": (c_int, [_P, _P, POINTER(EnvStepArgs), _P]),
     "jn_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),

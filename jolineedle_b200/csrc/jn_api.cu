@@ -238,11 +238,12 @@ constexpr int kXformWarps = 8;
 // Pipeline shape of the gather kernels: stages of the shared-memory ring, load lookahead (copy
 // kernel), bytes per chunk and resident CTAs per SM.  The defaults come from sweeps on B200
 // (tools/tune_gather.py, profiles/); JN_GATHER_TUNE="copy_stages,copy_ahead,copy_chunk_bytes,
-// copy_ctas_per_sm,xform_stages,xform_chunk_bytes,xform_ctas_per_sm" overrides them (0 keeps a
+// copy_ctas_per_sm,xform_stages,xform_chunk_bytes,xform_ctas_per_sm,xform_batch" overrides them (0 keeps a
 // default).
 struct GatherTune {
   int copy_stages = 6, copy_ahead = 3, copy_chunk = 32768, copy_ctas = 0;
   int xform_stages = 4, xform_chunk = 0, xform_ctas = 0;
+  int xform_batch = 4;  // chunks per ticket for the bulk of a launch (power of two <= 32), see claim_schedule
 };
 
 GatherTune gather_tune(int patch, int elem, bool plain_copy, bool focus, int engine) {
@@ -262,9 +263,12 @@ GatherTune gather_tune(int patch, int elem, bool plain_copy, bool focus, int eng
   t.copy_ctas = copy[bucket][3];
   const int(*x)[3] = elem == 4 ? f32_focus : (focus ? norm_focus : norm_plain);
   t.xform_stages = x[bucket][0]; t.xform_chunk = x[bucket][1]; t.xform_ctas = x[bucket][2];
+  // chunks per ticket: 4 with tensor tiles (one instruction per chunk), 8 with per-row bulk copies (lists of
+  // images: the producer issues a copy per row, a few more chunks per decode amortise that) -- r02 sweep
+  t.xform_batch = engine == JN_ENGINE_BULK ? 8 : 4;
   if (const char* env = getenv("JN_GATHER_TUNE")) {
-    int v[7] = {0, 0, 0, 0, 0, 0, 0};
-    sscanf(env, "%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6]);
+    int v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    sscanf(env, "%d,%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7]);
     if (v[0] > 0) t.copy_stages = v[0];
     if (v[1] > 0) t.copy_ahead = v[1];
     if (v[2] > 0) t.copy_chunk = v[2];
@@ -272,7 +276,11 @@ GatherTune gather_tune(int patch, int elem, bool plain_copy, bool focus, int eng
     if (v[4] > 0) t.xform_stages = v[4];
     if (v[5] > 0) t.xform_chunk = v[5];
     if (v[6] > 0) t.xform_ctas = v[6];
+    if (v[7] > 0) t.xform_batch = v[7];
   }
+  int b = 1;
+  while (b * 2 <= t.xform_batch && b < 32) b *= 2;  // power of two
+  t.xform_batch = b;
   (void)plain_copy;
   return t;
 }
@@ -310,16 +318,20 @@ int persistent_ctas_per_sm(Kernel kernel, int threads, size_t smem, int device, 
 
 // Ticket schedule of the converting gather (gather_xform_kernel): which chunks a ticket stands for.  The
 // producer claims tickets three batches ahead (that is what hides the decode latency), so a CTA that falls
-// behind still owns three batches when the tickets run out: batches are therefore SMALL -- 4 chunks for the bulk
-// of the launch, then per CTA three batches of 2 and six single chunks -- so that what a slow CTA still holds
-// (<= 12 chunks) is about what every other CTA draws from the fine-grained end (12 chunks).  (Batches of 32, one
-// chunk per producer lane, with the same look-ahead left a slow CTA 96 chunks behind: -5 % on cfg 3.)  A launch
-// too short for all of it drops the large sizes first.  Segments are stored in launch order.
-void claim_schedule(jnk::GatherArgs& a, int grid) {
-  constexpr int kHead = 4, kTail = 2;
-  static const int sizes[kTail] = {1, 2}, per_cta[kTail] = {6, 3};
-  int rem = a.total_chunks, counts[kTail] = {0, 0};
-  for (int j = 0; j < kTail && rem > 0; ++j) {
+// behind still owns three batches when the tickets run out.  The bulk of the launch goes out in batches of `head`
+// chunks (a power of two <= 32, picked per pipeline shape: GatherTune::xform_batch), followed, per CTA, by two
+// batches each of head/2 ... 4 chunks, three of 2 and six single chunks -- so that what a slow CTA still holds is
+// about what every other CTA draws from the fine-grained end.  A launch too short for all of it drops the large
+// sizes first.  Segments are stored in launch order.
+void claim_schedule(jnk::GatherArgs& a, int grid, int head) {
+  int sizes[5], per_cta[5], n_tail = 0;
+  for (int sz = 1; sz < head && n_tail < 5; sz *= 2) {
+    sizes[n_tail] = sz;
+    per_cta[n_tail] = sz == 1 ? 6 : sz == 2 ? 3 : 2;
+    ++n_tail;
+  }
+  int rem = a.total_chunks, counts[5] = {0, 0, 0, 0, 0};
+  for (int j = 0; j < n_tail && rem > 0; ++j) {
     long long want = (long long)per_cta[j] * grid;  // batches
     const bool all = want * sizes[j] <= rem;
     if (!all) want = rem / sizes[j];
@@ -333,8 +345,8 @@ void claim_schedule(jnk::GatherArgs& a, int grid) {
     a.sched_size[n] = size; a.sched_ticket[n] = ticket; a.sched_chunk[n] = chunk;
     ticket += batches; chunk += chunks; ++n;
   };
-  push(kHead, (rem + kHead - 1) / kHead, rem);  // head, the last batch possibly partial
-  for (int j = kTail - 1; j >= 0; --j) push(sizes[j], counts[j], counts[j] * sizes[j]);
+  push(head, (rem + head - 1) / head, rem);  // head, the last batch possibly partial
+  for (int j = n_tail - 1; j >= 0; --j) push(sizes[j], counts[j], counts[j] * sizes[j]);
   a.sched_n = n;
   for (int j = n; j < 7; ++j) { a.sched_ticket[j] = ticket; a.sched_chunk[j] = chunk; }
   for (int j = n; j < 6; ++j) a.sched_size[j] = 1;
@@ -342,7 +354,7 @@ void claim_schedule(jnk::GatherArgs& a, int grid) {
 
 template <typename Kernel, typename... Extra>
 int launch_persistent(Kernel kernel, const jnk::GatherArgs& args, const CUtensorMap& map, int threads, size_t smem,
-                      const DeviceInfo& dev, cudaStream_t stream, int ctas_cap, bool pdl, Extra... extra) {
+                      const DeviceInfo& dev, cudaStream_t stream, int ctas_cap, bool pdl, int batch, Extra... extra) {
   int per_sm = 0;
   if (int rc = persistent_ctas_per_sm(kernel, threads, smem, dev.device, &per_sm)) return rc;
   if (per_sm < 1) return fail(JN_ERR_CUDA, "gather kernel does not fit on an SM (%zu bytes of shared memory)", smem);
@@ -351,7 +363,7 @@ int launch_persistent(Kernel kernel, const jnk::GatherArgs& args, const CUtensor
   if (grid > args.total_chunks) grid = args.total_chunks;
   jnk::GatherArgs a = args;
   if (a.work_counter) {
-    claim_schedule(a, (int)grid);
+    claim_schedule(a, (int)grid, batch);
     if (a.sched_ticket[a.sched_n] < grid) grid = a.sched_ticket[a.sched_n];  // never more CTAs than tickets
   }
   JN_CUDA(launch_kernel(kernel, dim3((unsigned)grid), dim3((unsigned)threads), smem, stream, pdl, a, map, extra...));
@@ -592,10 +604,12 @@ int gather_launch(const jn_images* set, const GatherRequest& rq, cudaStream_t st
     if (!tma_mode || !out_aligned || !set->bulk_ok) engine = JN_ENGINE_LDG;
     else if (shifts || set->padded) engine = (shift_copy_ok || shift_xform_ok) ? JN_ENGINE_TENSOR : JN_ENGINE_LDG;
     else {
-      // tiles wider than one TMA box (P > 256: two or more boxes per row): per-row bulk copies measured 1-7 %
-      // faster than tensor tiles in every mode (profiles/r01/micro_quick_v2.jsonl); up to 256 the engines tie
-      // or the tensor tiles win
-      const bool prefer_bulk = set->kbox > 1;
+      // pure-DMA copy kernel, tiles wider than one TMA box (P > 256: two or more boxes per row): per-row bulk
+      // copies measured 1-7 % faster than tensor tiles (profiles/r01/micro_quick_v2.jsonl).  The converting
+      // kernel, whose producer feeds the ring in small batches, is better off with ONE tensor-tile instruction
+      // per chunk than with a bulk copy per row at every patch size (profiles/r02/sweep_batch_engine.jsonl:
+      // +2-12 % at P = 128 / 256 / 448, a tie at 1024)
+      const bool prefer_bulk = set->kbox > 1 && plain_copy;
       engine = (set->tensor_ok && set->n_slabs == 1 && !prefer_bulk) ? JN_ENGINE_TENSOR : JN_ENGINE_BULK;
     }
   }
@@ -660,9 +674,9 @@ int gather_launch(const jn_images* set, const GatherRequest& rq, cudaStream_t st
 #define JN_COPY(S, D)                                                                                              \
   if (tune.copy_stages == S && tune.copy_ahead == D)                                                               \
     return tensor ? launch_persistent(jnk::gather_copy_kernel<S, D, true>, a, map, 32, smem, dev, stream,          \
-                                      tune.copy_ctas, rq.pdl)                                                       \
+                                      tune.copy_ctas, rq.pdl, 1)                                                    \
                   : launch_persistent(jnk::gather_copy_kernel<S, D, false>, a, map, 32, smem, dev, stream,         \
-                                      tune.copy_ctas, rq.pdl);
+                                      tune.copy_ctas, rq.pdl, 1);
     JN_COPY(6, 3) JN_COPY(2, 1) JN_COPY(3, 1) JN_COPY(3, 2) JN_COPY(4, 1) JN_COPY(4, 2) JN_COPY(4, 3) JN_COPY(6, 2)
     JN_COPY(6, 4) JN_COPY(6, 5) JN_COPY(8, 4) JN_COPY(8, 6) JN_COPY(12, 6) JN_COPY(12, 9)
 #undef JN_COPY
@@ -678,9 +692,9 @@ int gather_launch(const jn_images* set, const GatherRequest& rq, cudaStream_t st
              a.stage_bytes);
 #define JN_XFORM(mode)                                                                                             \
   return shift_xform ? launch_persistent(jnk::gather_xform_kernel<mode, kXformWarps, true>, a, map, threads, smem, \
-                                         dev, stream, tune.xform_ctas, rq.pdl, stages, tensor)                     \
+                                         dev, stream, tune.xform_ctas, rq.pdl, tune.xform_batch, stages, tensor)   \
                      : launch_persistent(jnk::gather_xform_kernel<mode, kXformWarps, false>, a, map, threads, smem, \
-                                         dev, stream, tune.xform_ctas, rq.pdl, stages, tensor);
+                                         dev, stream, tune.xform_ctas, rq.pdl, tune.xform_batch, stages, tensor);
   if (normalize && !focus) { JN_XFORM(jnk::kNormPlain) }
   else if (normalize && focus) { JN_XFORM(jnk::kNormFocus) }
   else if (focus) { JN_XFORM(jnk::kF32Focus) }
@@ -704,13 +718,14 @@ int jn_gather(const jn_images* set, const int64_t* positions, const int32_t* src
 long long jn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // Host-only view of the converting gather's ticket schedule (tests: the tickets must tile [0, total) exactly).
-int jn_claim_schedule_host(int total_chunks, int grid, int32_t* sizes /*[6]*/, int32_t* tickets /*[7]*/,
+int jn_claim_schedule_host(int total_chunks, int grid, int batch, int32_t* sizes /*[6]*/, int32_t* tickets /*[7]*/,
                            int32_t* chunks /*[7]*/) {
   JN_REQUIRE(total_chunks >= 1 && grid >= 1 && sizes && tickets && chunks, "jn_claim_schedule_host: bad arguments");
+  JN_REQUIRE(batch >= 1 && batch <= 32 && (batch & (batch - 1)) == 0, "jn_claim_schedule_host: batch must be 1, 2, 4 ... 32");
   jnk::GatherArgs a;
   memset(&a, 0, sizeof(a));
   a.total_chunks = total_chunks;
-  claim_schedule(a, grid);
+  claim_schedule(a, grid, batch);
   for (int j = 0; j < 6; ++j) sizes[j] = a.sched_size[j];
   for (int j = 0; j < 7; ++j) { tickets[j] = a.sched_ticket[j]; chunks[j] = a.sched_chunk[j]; }
   return a.sched_n;

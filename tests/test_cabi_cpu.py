@@ -48,15 +48,16 @@ def test_gather_ticket_schedule_tiles_the_launch():
     rng = np.random.default_rng(0)
     cases = [(1, 1), (3, 3), (6144, 296), (43008, 148), (49152, 296), (31, 148), (296, 296), (297, 296), (1 << 20, 444)]
     cases += [(int(rng.integers(1, 200000)), int(rng.integers(1, 600))) for _ in range(200)]
-    for total, grid in cases:
+    for i, (total, grid) in enumerate(cases):
         grid = min(grid, total)
+        batch = (1, 2, 4, 8, 16, 32)[i % 6]
         sizes, tickets, chunks = (ctypes.c_int32 * 6)(), (ctypes.c_int32 * 7)(), (ctypes.c_int32 * 7)()
-        n = lib.jn_claim_schedule_host(total, grid, sizes, tickets, chunks)
+        n = lib.jn_claim_schedule_host(total, grid, batch, sizes, tickets, chunks)
         assert 1 <= n <= 6 and tickets[0] == 0 and chunks[0] == 0 and chunks[n] == total, (total, grid)
         covered, last_size = 0, 33
         for j in range(n):
             n_batches = tickets[j + 1] - tickets[j]
-            assert n_batches > 0 and 1 <= sizes[j] <= 4 and sizes[j] < last_size
+            assert n_batches > 0 and 1 <= sizes[j] <= batch and sizes[j] < last_size
             last_size = sizes[j]
             span = chunks[j + 1] - chunks[j]
             assert (n_batches - 1) * sizes[j] < span <= n_batches * sizes[j]  # only the last batch may be partial
@@ -64,8 +65,8 @@ def test_gather_ticket_schedule_tiles_the_launch():
             covered += span
         assert covered == total
         # the tail is fine-grained: a CTA never holds more than a few chunks when the tickets run out
-        if total >= 12 * grid:
-            assert sizes[n - 1] == 1 and tickets[n] - tickets[n - 1] == 6 * grid
+        if total >= 70 * grid and batch > 1:
+            assert sizes[0] == batch and sizes[n - 1] == 1 and tickets[n] - tickets[n - 1] == 6 * grid
 
 
 def test_invalid_arguments_are_reported_not_crashed():
