@@ -1,5 +1,14 @@
 #!/usr/bin/env python
-"""Scratch experiment: where does the time of a cfg-3 env step go?  (K1 alone vs the fused native call)"""
+"""Where does the time of an env step go?  K1 alone vs the fused native call, per engine / pipeline shape.
+
+    python tools/step_decomposition.py fused|split|contig [auto|tensor|bulk] [reinforce|aerial]
+    JN_PDL=0 python tools/step_decomposition.py fused            # without programmatic dependent launch
+    JN_GATHER_TUNE=0,0,0,0,stages,chunk_bytes,ctas,batch python tools/step_decomposition.py fused tensor
+
+fused  = the env's native step call (K2 + K1 behind it), CUDA events around each call;
+split  = the state update alone, then K1 by itself into the history slot (events around K1 only);
+contig = like split, into a fresh contiguous tensor.   Prints one JSON line (median / min / p90 over 4 rollouts);
+results of round 2: profiles/r02/step_decomposition.jsonl."""
 import json, os, sys, time
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
