@@ -288,6 +288,21 @@ int jn_visit_sources(const int64_t* positions, int32_t* first_slot, int n, int r
                      int t, int32_t* host_src, int32_t* history_src, int32_t* status, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Glimpse pyramid: one level of NeedleGeneralEnv.init_glimps_images (general_env.py:84-115) --
+ * TF.pad(level, [P]*4, "reflect") followed by TF.resize(.., [H, W], antialias=True) -- for float32 images.
+ * src: n_images images of [C, H, W] floats, src_image_stride_bytes apart; dst likewise; tmp: n_images*C*H*W
+ * floats of scratch.  first / count / weights ([size, k] float32) per axis are the antialiased bilinear filter
+ * taps of every output index over the PADDED axis (size + 2*pad -> size), computed by the host exactly as ATen
+ * does (jolineedle_b200/pyramid.py:aa_weights).  Rows pass, then columns pass, every output pixel the chain
+ * t = s0*w0, t = fma(s_j, w_j, t): bit-identical to torch's CPU kernel (AVX2 / AVX-512 builds).
+ * ------------------------------------------------------------------------------------------ */
+int jn_resize_aa_reflect(const float* src, int64_t src_image_stride_bytes, float* tmp, float* dst,
+                         int64_t dst_image_stride_bytes, int n_images, int channels, int height, int width,
+                         int pad, const int32_t* first_x, const int32_t* count_x, const float* weights_x,
+                         int k_x, const int32_t* first_y, const int32_t* count_y, const float* weights_y,
+                         int k_y, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K3  segmented scans.
  * ------------------------------------------------------------------------------------------ */
 /* Returns tail of a rollout (reinforce.py:186-202).  Inputs are step-major as the env

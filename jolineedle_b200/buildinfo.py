@@ -13,7 +13,7 @@ from . import _cabi
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # same list, same order as SRC + HDR of csrc/Makefile
 SOURCES = ["csrc/jn_api.cu", "csrc/jn_planner.cpp", "csrc/jn_device.cuh", "csrc/jn_gather.cuh", "csrc/jn_env.cuh",
-           "csrc/jn_scan.cuh", "../include/jolineedle_b200.h"]
+           "csrc/jn_scan.cuh", "csrc/jn_pyramid.cuh", "../include/jolineedle_b200.h"]
 
 
 def source_hash() -> str:

@@ -17,6 +17,8 @@ Extensions (keyword-only, default = reference behaviour):
              pixels with zero fill -- the ``--augment-translate`` augmentation (dataset.py:157-226,
              ``F.affine(translate=[tx, ty], fill=0)``) folded into the gather coordinates instead of a
              shifted copy of the image made on the CPU.  The caller shifts the boxes (as the dataset does).
+  (``n_glimps_levels > 1``: the glimpse pyramid of float32 images, bit-identical to the reference's CPU
+  torchvision pad + antialiased resize -- ``jolineedle_b200/pyramid.py``)
   device     upload CPU inputs to this CUDA device (the reference keeps everything on
              ``images.device``; there is no CPU path here)
   zero_copy  pinned HOST images are not uploaded: every step reads the glimpsed tiles in place over PCIe,
@@ -192,17 +194,12 @@ class NeedleGeneralEnv:
     def init_glimps_images(self, images: Tensor) -> Tensor:
         """Stack of progressively zoomed-out copies of the images (general_env.py:84-115): level 0 is the input,
         level k+1 = level k reflect-padded by one patch on every side and resized (antialiased bilinear) back to
-        H x W.  Built once per env with the same torchvision calls as the reference, on the GPU (library ops, not
-        on the step path); the per-step crops then come from all levels through the K1 gather.  The GPU resize
-        agrees with the reference's CPU resize to float rounding (~1e-7), not bit for bit."""
-        import torchvision.transforms.functional as TF
+        H x W.  Built once per env by ``jn_resize_aa_reflect`` (jolineedle_b200/pyramid.py): the reference's
+        torchvision CPU arithmetic restated tap by tap, so the levels -- and the crops the K1 gather then takes
+        from them -- equal the reference's bit for bit."""
+        from ..pyramid import build_levels
 
-        levels, current = [], images
-        for _ in range(self.n_glimps_levels):
-            levels.append(current)
-            current = TF.pad(current, padding=[self.patch_size] * 4, padding_mode="reflect")
-            current = TF.resize(current, size=[self.height, self.width], antialias=True)
-        return torch.stack(levels, dim=1).contiguous()
+        return build_levels(images, self.patch_size, self.n_glimps_levels)
 
     # ------------------------------------------------------------------------------------
     def _stream(self):

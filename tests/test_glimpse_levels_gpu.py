@@ -1,7 +1,6 @@
 """Multi-level glimpses (n_glimps_levels > 1, general_env.py:84-115) against a fixture of the unmodified
-reference.  Level 0 is a bit-exact crop; higher levels go through torchvision's antialiased resize, which on the
-GPU agrees with the reference's CPU result to float rounding: tolerance 2e-6 absolute on values in [0, 1]
-(the north star's 1e-6 relative for floats, widened by one ulp of 1.0 for the resampling sum)."""
+reference: every level -- built by jn_resize_aa_reflect, the reference's CPU torchvision pad + antialiased resize
+restated tap by tap -- and every crop taken from it, BIT for BIT."""
 import numpy as np
 import pytest
 import torch
@@ -9,8 +8,6 @@ import torch
 from helpers import load_golden, scenario, to_f32
 
 pytestmark = pytest.mark.gpu
-
-ATOL = 2e-6
 
 
 @pytest.mark.parametrize("name", ["lv2", "lv3"])
@@ -23,7 +20,7 @@ def test_glimpse_pyramid_matches_reference(name, history):
     env = NeedleGeneralEnv(to_f32(c["u8"]).cuda(), torch.from_numpy(c["boxes"]), 16, 6, levels, True, history=history)
     assert tuple(env.images.shape) == tuple(c["images"].shape)
     assert torch.equal(env.images[:, 0].cpu(), torch.from_numpy(c["images"][:, 0]))  # level 0 untouched
-    assert np.abs(env.images.cpu().numpy() - c["images"]).max() <= ATOL
+    assert np.array_equal(env.images.cpu().numpy(), c["images"])  # every level, bit for bit
     patches, _ = env.reset(torch.from_numpy(c["start"]))
     got = [patches]
     for t, a in enumerate(c["actions"]):
@@ -33,10 +30,26 @@ def test_glimpse_pyramid_matches_reference(name, history):
     for t, p in enumerate(got):
         want = c["patches"][t]
         assert tuple(p.shape) == tuple(want.shape) == (3, levels, 3, 16, 16)
-        assert torch.equal(p[:, 0].cpu(), torch.from_numpy(want[:, 0])), t  # level 0: bit-exact
-        assert np.abs(p.cpu().numpy() - want).max() <= ATOL, t
+        assert np.array_equal(p.cpu().numpy(), want), t
     if history:
         hist = env.patch_history()
         assert tuple(hist.shape) == (3, (len(c["actions"]) + 1) * levels, 3, 16, 16)
         assert torch.equal(hist[:, -levels:], got[-1])
     env.check_status()
+
+
+@pytest.mark.parametrize("P,gh,gw,levels", [(32, 4, 5, 3), (448, 5, 6, 2), (64, 7, 3, 4)])
+def test_pyramid_levels_equal_torchvision_cpu(P, gh, gw, levels):
+    """Other shapes (incl. the LARD geometry), straight against the reference's own calls on the CPU."""
+    import torchvision.transforms.functional as TF
+
+    from jolineedle_b200.pyramid import build_levels
+
+    g = torch.Generator().manual_seed(P + levels)
+    images = torch.randint(0, 256, (2, 3, gh * P, gw * P), dtype=torch.uint8, generator=g).float() / 255
+    want, cur = [images], images
+    for _ in range(levels - 1):  # general_env.py:95-111
+        cur = TF.resize(TF.pad(cur, padding=[P] * 4, padding_mode="reflect"), size=[gh * P, gw * P], antialias=True)
+        want.append(cur)
+    got = build_levels(images.cuda(), P, levels)
+    assert torch.equal(got.cpu(), torch.stack(want, dim=1))
