@@ -463,9 +463,10 @@ def reference_arm(args, rank, world):
 
 
 # ----------------------------------------------------------------------------------------------
-def ncu_traffic(workload_key, src, batch, default_batch, kernel_prefix):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
-    at its config batch -- only when the capture was taken from the sources the loaded library was built from."""
+def ncu_capture(workload_key, src, batch, default_batch, kernel_prefix):
+    """(DRAM bytes, duration in seconds, source note) of one launch of the dominant kernel from the committed
+    `ncu --set full` capture of this workload at its config batch -- only when the capture was taken from the
+    sources the loaded library was built from; (None, None, None) otherwise."""
     from jolineedle_b200 import buildinfo
 
     try:
@@ -474,13 +475,13 @@ def ncu_traffic(workload_key, src, batch, default_batch, kernel_prefix):
         name = f"{workload_key}_{src}"
         meta = summary.get("_meta", {}).get(name, {})
         if batch != default_batch or meta.get("source_hash") != buildinfo.library_source_hash():
-            return None, None
+            return None, None, None
         recs = [r for k_, v in summary[name].items() if k_.startswith(kernel_prefix) for r in v]
         rec = max(recs, key=lambda r: r["duration_s"])  # the trajectory / step gather (detection gathers are smaller)
-        return int(rec["dram_traffic_bytes"]), (f"profiles/{PROFILE_ROUND}/ncu_summary.json[{name}] (ncu --set full, "
-                                                f"source hash {meta['source_hash']})")
+        return int(rec["dram_traffic_bytes"]), float(rec["duration_s"]), (
+            f"profiles/{PROFILE_ROUND}/ncu_summary.json[{name}] (ncu --set full, source hash {meta['source_hash']})")
     except Exception:
-        return None, None
+        return None, None, None
 
 
 def measure_pcie(device, barrier, reps=4, nbytes=1 << 30):
@@ -565,7 +566,7 @@ def run_workload(wl_name, args, ctx, primary):
     gather_ms = {tag: round(sum(v) / len(v), 4) for tag, v in by_tag.items()}  # mean launch time of every gather
     gather_items = {tag: round(sum(v) / len(v), 1) for tag, v in items_by_tag.items()}
     prefix = "gather_xform_kernel" if src == "u8" else "gather_copy_kernel"
-    traffic, traffic_src = ncu_traffic(wl_name, src, batch, default_batch, prefix)
+    traffic, ncu_s, traffic_src = ncu_capture(wl_name, src, batch, default_batch, prefix)
     fused = wl_name != "supervised"
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
@@ -575,6 +576,9 @@ def run_workload(wl_name, args, ctx, primary):
                     "with programmatic dependent launch" if fused else ""),
                 "launches_timed": len(dur), "avg_launch_ms": round(sum(dur) / len(dur), 4) if dur else None,
                 "algorithmic_bytes_per_launch": int(sum(byts) / len(byts)) if byts else 0}
+    if ncu_s and byts:  # the kernel by itself (ncu's gpu__time_duration of the same capture): no launch latency, no K2
+        roofline["kernel_ms_ncu"] = round(ncu_s * 1e3, 4)
+        roofline["frac_kernel_ncu"] = round(sum(byts) / len(byts) / ncu_s / 1e9 / peak, 4)
     result = {"value": value, "ms_per_step": ms / args.steps, "roofline": roofline, "gpu_launches": launches,
               "host_ms_per_step": host_ms, "gather_ms_by_tag": gather_ms, "gather_items_by_tag": gather_items,
               "clocks": clocks.summary(t_begin, t_end) if rank == 0 else None}

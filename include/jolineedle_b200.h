@@ -230,11 +230,12 @@ int jn_env_props(const uint32_t* visited, const uint32_t* bbox, const uint8_t* h
 /* One call per env step: K2 followed by K1 without returning to the host language in between
  * (general_env.py:172-207 `step`, :144-170 `reset`).
  *
- * jn_env_step_gather launches the step kernel (as jn_env_step) and, behind it with programmatic dependent
- * launch, the gather of the new glimpses: tile (pos_out[i]) of image i -> out + i * out_item_stride_bytes.
- * The gather does not wait for the step kernel: it moves pos_in by the action itself (same move + clamp),
- * so both kernels run side by side and a step costs one launch latency.  pos_in and pos_out must not
- * alias.  `set` NULL or `out` NULL: state update only.
+ * jn_env_step_gather launches the gather of the new glimpses -- tile (pos_out[i]) of image i ->
+ * out + i * out_item_stride_bytes -- and the step kernel (as jn_env_step) as a programmatic-dependent-launch
+ * pair.  The gather does not need the step kernel: it moves pos_in by the action itself (same move + clamp).
+ * It is launched first and releases its dependents in its prologue, so the state update runs next to it and
+ * a step costs one launch latency.  pos_in and pos_out must not alias.  `set` NULL or `out` NULL: state
+ * update only.
  *
  * With a first-visit table (first_slot / host_src / history_src non-NULL; images in pinned HOST memory, crops
  * kept in a history buffer of `slots` slots per episode, `t` = the slot being written) the step kernel also

@@ -148,6 +148,7 @@ struct jn_images {
   jnk::ImageRec* d_recs = nullptr;
   bool owns_recs = true;
   bool padded = false;  // sizes are rounded up to the patch grid; pixels outside the image read as zeros
+  bool host_mapped = false;  // slab 0 is page-locked HOST memory: the gathers read it over PCIe
   // engines
   bool bulk_ok = false, tensor_ok = false;
   int box_w = 0, kbox = 0;
@@ -431,6 +432,11 @@ static int images_create(jn_images** out, int n_slabs, const void* const* slab_p
   s->patch = patch_size;
   s->padded = padded;
   cudaGetDevice(&s->device);
+  {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, slab_ptrs[0]) == cudaSuccess) s->host_mapped = attr.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+  }
   s->bulk_ok = aligned;
   s->box_w = aligned ? pick_box_width(patch_size, elem) : 0;
   s->kbox = s->box_w ? patch_size / s->box_w : 0;
@@ -610,7 +616,10 @@ int gather_launch(const jn_images* set, const GatherRequest& rq, cudaStream_t st
       // kernel, whose producer feeds the ring in small batches, is better off with ONE tensor-tile instruction
       // per chunk than with a bulk copy per row at every patch size (profiles/r02/sweep_batch_engine.jsonl:
       // +2-12 % at P = 128 / 256 / 448, a tie at 1024)
-      const bool prefer_bulk = set->kbox > 1 && plain_copy;
+      // Over PCIe (page-locked host images read in place) whole-row bulk copies keep the wider tiles at the
+      // link rate where tensor tiles of uint8 pixels lose a tenth (profiles/r02/zero_copy_pcie.jsonl: 50.1 vs
+      // 44.9 GB/s at P = 448).
+      const bool prefer_bulk = set->kbox > 1 && (plain_copy || set->host_mapped);
       engine = (set->tensor_ok && set->n_slabs == 1 && !prefer_bulk) ? JN_ENGINE_TENSOR : JN_ENGINE_BULK;
     }
   }
@@ -888,7 +897,7 @@ int launch_reset(const jnk::StepArgs& a, cudaStream_t stream) {
   return JN_OK;
 }
 
-int launch_step(const jnk::StepArgs& a, cudaStream_t stream) {
+int launch_step(const jnk::StepArgs& a, cudaStream_t stream, bool pdl = false) {
   DeviceInfo dev;
   if (int rc = current_device_info(dev)) return rc;
   // G lanes per episode in the bitmap phase: the power of two >= the number of bitmap words, at most a warp
@@ -896,7 +905,7 @@ int launch_step(const jnk::StepArgs& a, cudaStream_t stream) {
   while (g < a.words && g < 32) g <<= 1;
   const dim3 grid(grid_for(a.n, 64, dev.sm_count * 16)), block(64);  // a warp steps 32 episodes
 #define JN_STEP(G) \
-  case G: JN_CUDA(launch_kernel(jnk::env_step_kernel<G>, grid, block, 0, stream, false, a)); break;
+  case G: JN_CUDA(launch_kernel(jnk::env_step_kernel<G>, grid, block, 0, stream, pdl, a)); break;
   switch (g) { JN_STEP(1) JN_STEP(2) JN_STEP(4) JN_STEP(8) JN_STEP(16) JN_STEP(32) }
 #undef JN_STEP
   return JN_OK;
@@ -980,6 +989,18 @@ int jn_env_step_gather(const jn_images* set, const jn_images* history_set, const
   if (args->n == 0) return JN_OK;
   JN_REQUIRE(args->pos_in != args->pos_out || !set || !args->out,
              "jn_env_step_gather: pos_in and pos_out must not alias (the gather reads pos_in while the step runs)");
+  if (set && args->out && !args->first_slot) {
+    // The gather does not need the step kernel (it moves the old positions itself) and is the long one of the
+    // two: it goes FIRST, and the step kernel is launched behind it with the programmatic attribute -- the gather
+    // releases its dependents in its prologue -- so the state update runs next to the gather instead of in
+    // front of it.  The next step's launches are ordinary ones and wait for both.
+    GatherRequest rq;
+    rq.positions = args->pos_in; rq.actions = args->actions; rq.shifts = args->shifts; rq.n_items = args->n;
+    rq.out = args->out; rq.out_item_stride_bytes = args->out_item_stride_bytes; rq.flags = args->flags;
+    rq.engine = args->engine; rq.status = args->status; rq.grid_rows = args->rows; rq.grid_cols = args->cols;
+    if (int rc = gather_launch(set, rq, (cudaStream_t)stream)) return rc;
+    return launch_step(to_step_args(args), (cudaStream_t)stream, true);
+  }
   if (int rc = launch_step(to_step_args(args), (cudaStream_t)stream)) return rc;
   return gather_after(set, history_set, args, true, (cudaStream_t)stream);
 }

@@ -19,16 +19,32 @@ __global__ void returns_kernel(const float* __restrict__ rewards_tn, const uint8
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   double acc = 0.0;
-  for (int t = T - 1; t >= 0; --t) {
-    const float r = rewards_tn[(long long)t * n + e];
-    // logit_masks[:, t] = masks[:, t]: column 0 is True, column t = !terminated after step t-1
-    const uint8_t alive = (t == 0) ? 1 : (terminated_tn[(long long)(t - 1) * n + e] ? 0 : 1);
-    const float term = __fmul_rn(r, alive ? 1.0f : 0.0f);  // fp32 product first (keeps -0.0 / NaN behaviour)
-    acc += (double)term;
-    returns[(long long)e * T + t] = (float)acc;
-    rewards_out[(long long)e * T + t] = r;
-    logit_masks[(long long)e * T + t] = alive;
-    masks[(long long)e * (T + 1) + t + 1] = terminated_tn[(long long)t * n + e] ? 0 : 1;
+  // blocks of 8 steps from the last one backwards: the loads of a block are independent of the running sum and
+  // go out together; only the additions are serial
+  constexpr int kBlock = 8;
+  for (int hi = T; hi > 0; hi -= kBlock) {
+    const int lo = hi > kBlock ? hi - kBlock : 0;
+    float r[kBlock];
+    uint8_t term[kBlock + 1];  // term[k] = terminated after step lo + k - 1 (slot 0: the step before the block)
+#pragma unroll
+    for (int k = 0; k < kBlock; ++k)
+      if (lo + k < hi) r[k] = rewards_tn[(long long)(lo + k) * n + e];
+#pragma unroll
+    for (int k = 0; k <= kBlock; ++k)
+      if (lo + k <= hi) term[k] = (lo + k == 0) ? 0 : terminated_tn[(long long)(lo + k - 1) * n + e];
+#pragma unroll
+    for (int k = kBlock - 1; k >= 0; --k) {
+      const int t = lo + k;
+      if (t >= hi) continue;
+      // logit_masks[:, t] = masks[:, t]: column 0 is True, column t = !terminated after step t-1
+      const uint8_t alive = term[k] ? 0 : 1;
+      const float product = __fmul_rn(r[k], alive ? 1.0f : 0.0f);  // fp32 product first (keeps -0.0 / NaN behaviour)
+      acc += (double)product;
+      returns[(long long)e * T + t] = (float)acc;
+      rewards_out[(long long)e * T + t] = r[k];
+      logit_masks[(long long)e * T + t] = alive;
+      masks[(long long)e * (T + 1) + t + 1] = term[k + 1] ? 0 : 1;
+    }
   }
   masks[(long long)e * (T + 1)] = 1;
 }
