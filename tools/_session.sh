@@ -1,8 +1,6 @@
-D=gpurun_out/${1:-n2}; mkdir -p $D
-N=${2:-2}
-SECONDS=0
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > $D/bench_n$N.json 2> $D/bench_n$N.err; echo "bench N=$N rc=$? (${SECONDS}s)"
-SECONDS=0
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $N --steps 3 --warmup 1 > $D/ref_n$N.json 2> $D/ref_n$N.err; echo "reference N=$N rc=$? (${SECONDS}s)"
-{ nvidia-smi topo -m; lscpu | grep -iE "model name|socket|numa|^cpu\(s\)"; free -g | head -2; } > $D/topo.txt 2>&1
-tail -2 $D/bench_n$N.err
+D=gpurun_out/${1:-t1}; mkdir -p $D
+timeout 1200 python tools/tune_gather.py --skip-copy --out $D/tune_xform.jsonl > $D/tune_xform.txt 2>&1; echo "tune rc=$?"
+timeout 600 python tools/tune_gather.py --skip-copy --translate --patches 256,448 --out $D/tune_xform_tr.jsonl > $D/tune_xform_tr.txt 2>&1; echo "tune tr rc=$?"
+timeout 600 python tools/tune_gather.py --skip-copy --crop-gb 0.2 --patches 256 --out $D/tune_xform_small.jsonl > $D/tune_xform_small.txt 2>&1; echo "tune small rc=$?"
+timeout 600 python tools/tune_gather.py --skip-copy --crop-gb 0.2 --translate --patches 256 --out $D/tune_xform_small_tr.jsonl > $D/tune_xform_small_tr.txt 2>&1; echo "tune small tr rc=$?"
+echo done
