@@ -5,10 +5,13 @@
 //                  copies) in, one TMA bulk store per stage out.  No thread touches a pixel.
 //                  Chunks are dealt round-robin to a persistent grid (q = blockIdx.x + j * gridDim.x).
 //   xform  kernel: uint8 -> float32 normalisation, the Focus space-to-depth layout, translated
-//                  and / or virtually padded sources.  Warp 0 is the TMA producer: it claims
-//                  chunks from a global counter, decodes 32 of them in parallel (one per lane) a
-//                  batch ahead, and hands every stage a descriptor through shared memory; the
+//                  and / or virtually padded sources.  Warp 0 is the TMA producer: it draws
+//                  tickets (small batches of chunks) from a global counter three batches ahead,
+//                  decodes them as a software pipeline (no load is consumed in the iteration
+//                  that issued it) and hands every stage a descriptor through shared memory; the
 //                  other warps read the staged chunk, convert, and write coalesced vector stores.
+//                  With `actions` it also applies an env step's move to the positions it reads
+//                  (jn_env_step_gather), which makes it independent of the step kernel.
 //   rows   kernel: plain loads, one warp per tile row: what the TMA unit cannot address --
 //                  lists of images combined with a translation or padding, uint8 -> uint8 copies
 //                  with unaligned offsets.
@@ -215,11 +218,10 @@ gather_copy_kernel(const __grid_constant__ GatherArgs a, const __grid_constant__
 // Warp 0 is the TMA producer; the consumer warps read the staged chunk from shared memory,
 // convert and write coalesced vector stores.
 //
-//  * The producer decodes 32 chunks at a time (one per lane: the dependent loads src_index ->
-//    image record / position cost one latency per 32 chunks instead of one per chunk) and hands
-//    each stage a 16-byte descriptor through shared memory, so no consumer touches the index
-//    arrays.  The descriptor is written before the producer's arrive on the stage's `full`
-//    barrier (release) and read after the consumers' wait (acquire).
+//  * The producer decodes a ticket's chunks one per lane and hands each stage a 16-byte
+//    descriptor through shared memory, so no consumer touches the index arrays.  The descriptor
+//    is written before the producer's arrive on the stage's `full` barrier (release) and read
+//    after the consumers' wait (acquire).
 //  * kShift: integer translation with ANY x offset.  The TMA unit only takes 16-byte aligned
 //    inner coordinates, so the producer loads the aligned superset of each row (P*elem + 16
 //    bytes, 3-D map of 8-byte elements, out-of-image bytes arrive as zeros) and the consumers

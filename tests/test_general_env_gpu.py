@@ -229,3 +229,66 @@ def test_cfg4_geometry_8192_patch256_seq32():
     assert np.array_equal(env.visited_patches.cpu().numpy(), orc.visited)
     assert np.array_equal(env.prop_patches_found.cpu().numpy(), orc.prop_patches_found())
     env.check_status()
+
+
+@pytest.mark.parametrize("gh,gw", [(40, 36), (33, 33), (6, 11), (1, 70)])
+def test_grids_of_more_than_32_bitmap_words(gh, gw):
+    """Grids beyond 1024 patches (40x36 = 45 bitmap words: the step kernel's lanes loop over the words), just
+    past it (33x33 = 35 words), three words, and a single row of 70 patches -- every output against the oracle."""
+    b, P, T = 37, 8, 12  # 37 episodes: two warps of the lane-per-episode kernel, the second one partial
+    rng = np.random.default_rng(gh * 100 + gw)
+    u8 = synth_u8(b, 3, gh * P, gw * P, salt=gh)
+    images = to_f32(u8)
+    boxes = random_boxes(rng, b, 3, gh * P, gw * P, 9 * P)
+    for stop in (True, False):
+        orc = GazeOracle(images, boxes, P, T, 1, stop)
+        env = make_env(torch.from_numpy(u8).cuda(), torch.from_numpy(boxes), P, T, 1, stop, normalize=True)
+        assert np.array_equal(env.bbox_masks.cpu().numpy(), orc.bbox_masks)
+        torch.manual_seed(gw); p_o, i_o = orc.reset()
+        torch.manual_seed(gw); p_e, i_e = env.reset()
+        assert torch.equal(p_e.cpu(), p_o) and np.array_equal(i_e["positions"].cpu().numpy(), i_o["positions"])
+        for t in range(T):
+            a = rng.integers(0, 9 if stop else 8, size=b).astype(np.int64)
+            o, e = orc.step(a), env.step(torch.from_numpy(a))
+            assert torch.equal(e[0].cpu(), o[0]), t
+            for k in (1, 2, 3):
+                assert np.array_equal(e[k].cpu().numpy(), o[k]), (t, k)
+            assert np.array_equal(e[4]["positions"].cpu().numpy(), o[4]["positions"])
+        assert np.array_equal(env.visited_patches.cpu().numpy(), orc.visited)
+        assert np.array_equal(env.prop_patches_found.cpu().numpy(), orc.prop_patches_found())
+        assert np.array_equal(env.terminated.cpu().numpy(), orc.terminated())
+        env.check_status()
+
+
+def test_stepping_past_max_ep_len_and_rebound_positions():
+    """The reference env keeps stepping after truncation (truncated stays True) and lets callers move it by hand
+    (apply_movements rebinds env.positions): the per-episode rings roll over, results stay those of the oracle,
+    and tensors handed out earlier are never overwritten."""
+    b, P, gh, gw, T = 5, 16, 4, 5, 3
+    rng = np.random.default_rng(77)
+    u8 = synth_u8(b, 3, gh * P, gw * P, salt=2)
+    boxes = random_boxes(rng, b, 2, gh * P, gw * P, 2 * P)
+    orc = GazeOracle(to_f32(u8), boxes, P, T, 1, True)
+    env = make_env(to_f32(u8).cuda(), torch.from_numpy(boxes), P, T, 1, True)
+    start = np.stack([rng.integers(0, gh, b), rng.integers(0, gw, b)], 1).astype(np.int64)
+    orc.reset(start); env.reset(torch.from_numpy(start))
+    kept = []
+    for t in range(3 * T + 2):
+        a = rng.integers(0, 9, size=b).astype(np.int64)
+        if t == 4:  # move by hand between two steps, like a caller driving the pieces itself
+            env.apply_movements(torch.from_numpy(a).cuda())
+            moved = orc.positions + np.array([(0, -1), (0, 1), (-1, 0), (1, 0), (-1, -1), (-1, 1), (1, -1), (1, 1), (0, 0)])[a]
+            moved[:, 0] = np.clip(moved[:, 0], 0, gh - 1); moved[:, 1] = np.clip(moved[:, 1], 0, gw - 1)
+            orc.positions = moved
+            orc.has_stopped |= a == 8
+            a = rng.integers(0, 9, size=b).astype(np.int64)
+        o, e = orc.step(a), env.step(torch.from_numpy(a))
+        assert torch.equal(e[0].cpu(), o[0]), t
+        for k in (1, 2, 3):
+            assert np.array_equal(e[k].cpu().numpy(), o[k]), (t, k)
+        assert np.array_equal(e[4]["positions"].cpu().numpy(), o[4]["positions"])
+        kept.append((e[1], e[4]["positions"], o[1].copy(), o[4]["positions"].copy()))
+    for r, p, r_o, p_o in kept:  # every step's tensors still hold that step's values
+        assert np.array_equal(r.cpu().numpy(), r_o) and np.array_equal(p.cpu().numpy(), p_o)
+    with pytest.raises(RuntimeError):
+        env.rollout_buffers()  # the rings only hold the last steps of an episode that ran past max_ep_len
