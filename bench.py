@@ -572,7 +572,7 @@ def run_workload(wl_name, args, ctx, primary):
                 "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": f"{peak_kind} (MEASURED_PEAKS.json)",
                 "kernel": f"{prefix} (K1), tag={wl.main_tag}" + (
-                    "; events bracket the native step call: env_step_kernel + the gather launched behind it "
+                    "; events bracket the native step call: the gather + env_step_kernel launched behind it "
                     "with programmatic dependent launch" if fused else ""),
                 "launches_timed": len(dur), "avg_launch_ms": round(sum(dur) / len(dur), 4) if dur else None,
                 "algorithmic_bytes_per_launch": int(sum(byts) / len(byts)) if byts else 0}
