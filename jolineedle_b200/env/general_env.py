@@ -522,47 +522,61 @@ class NeedleGeneralEnv:
 
     @torch.no_grad()
     def get_detection_batch(self, sample_neg: int = 1):  # general_env.py:506-546
+        """Every (patch, box) hit + ``sample_neg`` random misses per image, gathered by K1.  The reference walks
+        the images in python (two ``torch.where``, a ``randperm``, two ``cat`` per image: ~40 ms at 1024 images);
+        here only the ``torch.randperm`` calls stay per image -- same CPU generator, same order, so the same
+        negatives are drawn -- and the bookkeeping is one vectorised pass over the presence table."""
+        import numpy as np
+
         local, present = self.parse_bboxes()
         present = present.squeeze(-1)  # only collapses when there is a single box per image (reference quirk)
-        present_host = present.cpu()
-        img_ids: List[int] = []
-        rows_ids: List[Tensor] = []
-        cols_ids: List[Tensor] = []
-        for i in range(self.batch_size):
-            hits = torch.where(present_host[i])
-            misses = torch.where(~present_host[i])
-            pick = torch.randperm(len(misses[0]))[:sample_neg]  # CPU generator, one draw per image
-            misses = tuple(m[pick] for m in misses)
-            r = torch.cat((hits[0], misses[0]))
-            c = torch.cat((hits[1], misses[1]))
-            rows_ids.append(r)
-            cols_ids.append(c)
-            img_ids.extend([i] * len(r))
-        r_all, c_all = torch.cat(rows_ids), torch.cat(cols_ids)
-        positions = torch.stack((r_all, c_all), dim=1).to(self.device)
-        src = torch.tensor(img_ids, dtype=torch.int32, device=self.device)
+        table = present.cpu().numpy()
+        b = self.batch_size
+        flat = table.reshape(b, -1)  # row-major like torch.where: (row, col[, box])
+        inner = flat.shape[1] // (self.n_vertical_patches * self.n_horizontal_patches)
+        hit_img, hit_cell = np.nonzero(flat)
+        miss_img, miss_cell = np.nonzero(~flat)
+        n_miss = np.bincount(miss_img, minlength=b)
+        miss_start = np.concatenate(([0], np.cumsum(n_miss)[:-1]))
+        picks = [torch.randperm(int(n))[:sample_neg] for n in n_miss]  # CPU generator, one draw per image
+        pick_img = np.repeat(np.arange(b), [len(p) for p in picks])
+        pick_cell = miss_cell[np.concatenate([p.numpy() + s for p, s in zip(picks, miss_start)])] if len(pick_img) else \
+            np.zeros(0, dtype=np.int64)
+        img_all = np.concatenate((hit_img, pick_img))
+        cell_all = np.concatenate((hit_cell, pick_cell))
+        order = np.argsort(img_all * 2 + np.concatenate((np.zeros(len(hit_img), np.int64), np.ones(len(pick_img), np.int64))),
+                           kind="stable")  # per image: its hits (table order), then its negatives (draw order)
+        img_all, cell_all = img_all[order], cell_all[order] // inner
+        host = np.empty((len(img_all), 3), dtype=np.int64)
+        host[:, 0] = cell_all // self.n_horizontal_patches
+        host[:, 1] = cell_all % self.n_horizontal_patches
+        host[:, 2] = img_all
+        dev_idx = torch.from_numpy(host).to(self.device)
+        positions = dev_idx[:, :2].contiguous()
+        src_l = dev_idx[:, 2].contiguous()
+        src = src_l.to(torch.int32)
         # glimpse level 0 of image i is image i*G of the stacked set (general_env.py:533-539)
         patches = self._set.gather(positions, src_index=src * self.n_glimps_levels, normalize=self._normalize,
                                    engine=self._engine, status=self._status, shifts=self._shifts,
                                    shifts_aligned=self._shifts_aligned)
-        src_l = src.long()
         boxes = local[src_l, positions[:, 0], positions[:, 1]]  # [n, N, 4]
         boxes = torch.nn.functional.pad(boxes, (1, 0))  # class id 0 in front
         return patches, boxes
 
     @torch.no_grad()
     def get_detection_targets(self) -> List[Tensor]:  # general_env.py:548-573
+        """Global-coordinate split boxes per image (all-zero entries skipped, general_env.py:560), row-major over
+        (y, x, k) like the reference's loops: one masked select for the whole batch and one split, instead of a
+        masked select (= a device synchronisation) per image."""
         local, _ = self.parse_bboxes()
         rows, cols, p = self.n_vertical_patches, self.n_horizontal_patches, self.patch_size
         ys = torch.arange(rows, device=self.device).view(1, rows, 1, 1)
         xs = torch.arange(cols, device=self.device).view(1, 1, cols, 1)
         offset = torch.stack((xs.expand(1, rows, cols, 1), ys.expand(1, rows, cols, 1)) * 2, dim=-1) * p
         glob = local + offset  # x1+ox, y1+oy, x2+ox, y2+oy
-        keep = local.abs().sum(dim=-1) != 0  # all-zero entries are skipped (general_env.py:560)
-        out = []
-        for i in range(self.batch_size):
-            sel = glob[i][keep[i]]  # row-major over (y, x, k): the reference's loop order
-            if sel.shape[0] == 0:
-                raise RuntimeError("stack expects a non-empty TensorList")  # what torch.stack([]) raises
-            out.append(torch.nn.functional.pad(sel, (1, 0)))
-        return out
+        keep = local.abs().sum(dim=-1) != 0
+        counts = keep.view(self.batch_size, -1).sum(dim=1).tolist()
+        if 0 in counts:
+            raise RuntimeError("stack expects a non-empty TensorList")  # what torch.stack([]) raises in the reference
+        chosen = torch.nn.functional.pad(glob[keep], (1, 0))  # class id 0 in front; batch-major, then (y, x, k)
+        return list(torch.split(chosen, counts))
