@@ -293,6 +293,26 @@ def _upload(array: np.ndarray, device) -> torch.Tensor:
     return staged.to(device, non_blocking=True)
 
 
+def _upload_blocks(arrays: Sequence[np.ndarray], device) -> List[torch.Tensor]:
+    """Several host arrays -> device in ONE pinned staging buffer and ONE asynchronous copy (a batch used to
+    pay four pinned allocations and four copies); returns one typed, 16-byte aligned view per array."""
+    offsets, total = [], 0
+    for a in arrays:
+        offsets.append(total)
+        total += -(-a.nbytes // 16) * 16
+    staged = torch.empty(max(total, 16), dtype=torch.uint8, pin_memory=True)
+    host = staged.numpy()
+    for a, off in zip(arrays, offsets):
+        if a.nbytes:
+            host[off:off + a.nbytes] = np.ascontiguousarray(a).reshape(-1).view(np.uint8)
+    dev = staged.to(device, non_blocking=True)
+    out = []
+    for a, off in zip(arrays, offsets):
+        dtype = torch.from_numpy(a[:0].reshape(-1)).dtype
+        out.append(dev[off:off + a.nbytes].view(dtype).view(a.shape))
+    return out
+
+
 
 def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normalize: bool = False,
                   engine: str = "auto", reuse_glimpses: bool = True) -> Dict[str, torch.Tensor]:
@@ -311,10 +331,11 @@ def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normaliz
                           p.cols, p.n_boxes, det_src])
     u8 = np.concatenate([p.seg_flags, p.draws, np.zeros(1, dtype=np.uint8)])
     i64 = np.concatenate([p.boxes.ravel(), p.det_yx.astype(np.int64).ravel()])
-    d_i32, d_u8, d_i64 = (_upload(a, dev) for a in (i32, u8, i64))
     # boxes that are not whole pixels: labels and local boxes from the float64 coordinates (python planner only)
     float_boxes = p.boxes_f64 is not None
-    d_boxes_f64 = _upload(p.boxes_f64, dev) if float_boxes else None
+    blocks = _upload_blocks([i32, u8, i64] + ([p.boxes_f64] if float_boxes else []), dev)
+    d_i32, d_u8, d_i64 = blocks[:3]
+    d_boxes_f64 = blocks[3] if float_boxes else None
     patch_bitmaps = lib.jn_patch_bitmaps_f64 if float_boxes else lib.jn_patch_bitmaps
     local_boxes = lib.jn_local_boxes_f64 if float_boxes else lib.jn_local_boxes
 

@@ -5,7 +5,8 @@ An :class:`ImageSet` borrows one ``[B, C, H, W]`` CUDA tensor, or a list of ``[C
 of them.  No pixel is copied at construction; the tensors are kept alive by the handle.
 """
 import ctypes
-from typing import List, Optional, Sequence, Union
+from operator import attrgetter
+from typing import Dict, List, Optional, Sequence, Union
 
 import numpy as np
 import torch
@@ -38,6 +39,19 @@ class LaunchTimer:
 TIMING: Optional[LaunchTimer] = None
 
 
+_DTYPE_OF = attrgetter("dtype")
+_STREAMS: Dict[tuple, "torch.cuda.Stream"] = {}
+
+
+def _stream_object(device, raw: int):
+    """torch Stream object of the current raw stream (building one costs ~25 us: cached per handle)."""
+    key = (device.index, raw)
+    stream = _STREAMS.get(key)
+    if stream is None:
+        stream = _STREAMS[key] = torch.cuda.current_stream(device)
+    return stream
+
+
 class ImageSet:
     def __init__(self, images: Union[torch.Tensor, Sequence[torch.Tensor]], patch_size: int, device=None,
                  pad_to_patch: bool = False):
@@ -56,7 +70,7 @@ class ImageSet:
         first = slabs[0]
         dtype, channels = first.dtype, first.shape[-3]
         shapes = [t.shape for t in slabs]
-        if any(len(sh) not in (3, 4) for sh in shapes):
+        if not set(map(len, shapes)) <= {3, 4}:
             bad = next(sh for sh in shapes if len(sh) not in (3, 4))
             raise ValueError(f"images must be [C,H,W] or [B,C,H,W], got shape {tuple(bad)}")
         where = [t.get_device() for t in slabs]  # CUDA device index, -1 for host tensors
@@ -66,7 +80,7 @@ class ImageSet:
                 if d < 0 and (device is None or not t.is_pinned()):
                     _cabi.require_cuda(t, "images")
         devices = {d for d in where if d >= 0}
-        if len(devices) > 1 or any(t.dtype != dtype for t in slabs) or any(sh[-3] != channels for sh in shapes):
+        if len(devices) > 1 or set(map(_DTYPE_OF, slabs)) != {dtype} or {sh[-3] for sh in shapes} != {channels}:
             raise ValueError("all images of a set must share device, dtype and channel count")
         cuda_device = torch.device("cuda", next(iter(devices))) if devices else None
         for t, d in zip(slabs, where):
@@ -113,9 +127,10 @@ class ImageSet:
             if rc == _cabi.JN_OK and self._table is not None:
                 self._table.copy_(self._table_host, non_blocking=True)
                 # gathers on OTHER streams must not run before this copy: they wait for the event once each
+                raw = _cabi.stream_ptr(self.device)
                 self._table_ready = torch.cuda.Event()
-                self._table_ready.record()
-                self._table_streams.add(_cabi.stream_ptr(self.device))
+                self._table_ready.record(_stream_object(self.device, raw))
+                self._table_streams.add(raw)
         # same precondition as the reference envs: sizes must be multiples of the patch size
         _cabi.check(rc, invalid_exc=AssertionError)
         self._handle = handle
