@@ -315,7 +315,7 @@ def _upload_blocks(arrays: Sequence[np.ndarray], device) -> List[torch.Tensor]:
 
 
 def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normalize: bool = False,
-                  engine: str = "auto", reuse_glimpses: bool = True) -> Dict[str, torch.Tensor]:
+                  engine: str = "auto", reuse_glimpses: bool = True, focus: bool = False) -> Dict[str, torch.Tensor]:
     """Packed plans -> the collated sample dict of the reference (keys ``patches``,
     ``current_actions``, ``next_actions``, ``positions``, ``masks``, ``labels``, ``local_bboxes``,
     ``patches_yolox``, ``bboxes_yolox``; plus ``_ep_len`` / ``_status`` for diagnostics)."""
@@ -359,7 +359,7 @@ def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normaliz
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     area = torch.empty((n, words), dtype=torch.int32, device=dev)
     out = {
-        "patches": torch.empty((n, T) + image_set.out_shape(1, False)[1:], dtype=torch.float32, device=dev),
+        "patches": torch.empty((n, T) + image_set.out_shape(1, focus)[1:], dtype=torch.float32, device=dev),
         "current_actions": torch.empty((n, T), dtype=torch.long, device=dev),
         "next_actions": torch.empty((n, T), dtype=torch.long, device=dev),
         "positions": torch.empty((n, T, 2), dtype=torch.long, device=dev),
@@ -393,31 +393,31 @@ def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normaliz
         # Host-resident images: a walk with detours revisits patches (~10 % of the slots); those tiles are
         # copied inside HBM from their first occurrence instead of crossing PCIe again.  The trajectory
         # buffer doubles as a set of n*T one-patch images for that (and for the detection patches below).
-        reuse_set = ImageSet(traj_tiles, P)
+        reuse_set = ImageSet(traj_tiles, traj_tiles.shape[-1])  # one-patch images (P, or P/2 in the Focus layout)
         first_src = torch.empty((n * T,), dtype=torch.int32, device=dev)
         repeat_src = torch.empty((n * T,), dtype=torch.int32, device=dev)
         with _cabi.on_device(dev):
             _cabi.check(lib.jn_tile_dedupe(out["positions"].data_ptr(), gather_src.data_ptr(), n * T, T,
                                            first_src.data_ptr(), repeat_src.data_ptr(), stream))
         image_set.gather(out["positions"].view(n * T, 2), src_index=first_src, out=traj_tiles, normalize=normalize,
-                         engine=engine, status=status, tag="trajectory")
+                         focus=focus, engine=engine, status=status, tag="trajectory")
         reuse_set.gather(None, src_index=repeat_src, out=traj_tiles, engine=engine, status=status,
                          tag="trajectory-reuse")
         out["_host_traj_tiles"] = (first_src >= 0).sum()  # trajectory tiles that did cross PCIe
     else:
         image_set.gather(out["positions"].view(n * T, 2), src_index=gather_src.view(n * T), out=traj_tiles,
-                         normalize=normalize, engine=engine, status=status, tag="trajectory")
+                         normalize=normalize, focus=focus, engine=engine, status=status, tag="trajectory")
     # detection patches: every box patch + one random empty patch per image (simple_env.py:397-441)
     # (the number of detection patches varies from batch to batch, and a buffer of a new size is a fresh
     # multi-GB cudaMalloc -- tens of milliseconds -- for torch's caching allocator.  So the capacity only
     # ever grows, with 1/8 headroom, per (device, tile shape, batch size): after the first batches every request has the
     # same size and is served from the cache; the result is a view of the buffer's head)
-    key = (dev, image_set.channels, P, n)
+    key = (dev, image_set.channels, P, n, focus)
     need = max(n_det, 1)
     det_cap = _det_capacity.get(key, 0)
     if need > det_cap:
         det_cap = _det_capacity[key] = -(-(need + need // 8) // 64) * 64
-    det_buf = torch.empty(image_set.out_shape(det_cap, False), dtype=torch.float32, device=dev)
+    det_buf = torch.empty(image_set.out_shape(det_cap, focus), dtype=torch.float32, device=dev)
     if reuse_set is not None and n_det > 0:
         # Host-resident images: most detection patches were just gathered as trajectory glimpses, so take
         # those from the [n*T, C, P, P] buffer in HBM instead of pulling them over PCIe a second time: two
@@ -431,14 +431,16 @@ def expand_packed(image_set: ImageSet, p: PackedPlans, max_ep_len: int, normaliz
                                            pos2.data_ptr(), src2.data_ptr(), stream))
         minus_one, n_img = torch.full_like(src2, -1), image_set.n_images
         image_set.gather(pos2, src_index=torch.where(src2 < n_img, src2, minus_one), out=det_buf[:n_det],
-                         normalize=normalize, engine=engine, status=status, tag="detection", skip_negative=True)
+                         normalize=normalize, focus=focus, engine=engine, status=status, tag="detection",
+                         skip_negative=True)
         reuse_set.gather(pos2, src_index=torch.where(src2 >= n_img, src2 - n_img, minus_one), out=det_buf[:n_det],
                          engine=engine, status=status, tag="detection-reuse", skip_negative=True)
         out["patches_yolox"] = det_buf[:n_det]
         out["_host_det_tiles"] = (src2 < image_set.n_images).sum()  # detection tiles that did cross PCIe
     else:
         out["patches_yolox"] = image_set.gather(d_det_pos, src_index=d_det_src, out=det_buf[:n_det],
-                                                normalize=normalize, engine=engine, status=status, tag="detection")
+                                                normalize=normalize, focus=focus, engine=engine, status=status,
+                                                tag="detection")
     det_boxes = torch.empty((n_det, n_max, 6), dtype=torch.float32, device=dev)
     if n_max > 0 and n_det > 0:
         with _cabi.on_device(dev):
@@ -510,6 +512,7 @@ def generate_trajectories(
     zero_copy: bool = True,
     stats: Optional[dict] = None,
     check: bool = False,
+    focus: bool = False,
 ) -> Dict[str, torch.Tensor]:
     """Batched supervised trajectories (``SupervisedTrainer.generate_trajectories``,
     supervised.py:95-136): ``batch`` holds lists ``image`` ([C,H,W] tensors), ``bboxes`` (lists
@@ -517,7 +520,9 @@ def generate_trajectories(
     ``seeds`` (one per image) makes the plans reproducible; the reference builds unseeded envs.
     CPU images are uploaded to ``device`` first (there is no CPU path).  ``check`` synchronises and raises if
     a kernel flagged its input (a position outside the grid, a plan the expansion could not follow); without it
-    the flags travel in ``stats["status"]`` and nothing waits for the device."""
+    the flags travel in ``stats["status"]`` and nothing waits for the device.  ``focus``: ``patches`` and
+    ``patches_yolox`` come out in the YOLOX Focus space-to-depth layout ``[4C, P/2, P/2]`` (what the detector's
+    stem computes first), written that way by the gather itself."""
     images: List[torch.Tensor] = list(batch["image"])
     if device is not None:
         # Pinned host images are NOT uploaded: a supervised episode looks at ~10 of an image's 30
@@ -531,7 +536,7 @@ def generate_trajectories(
         image_set = ImageSet(images, patch_size, device=device)  # while the native planner runs on its own thread
     finally:
         packed = plans()  # always joined: the planner reads arrays that die with this frame
-    out = expand_packed(image_set, packed, max_seq_len, normalize, engine)
+    out = expand_packed(image_set, packed, max_seq_len, normalize, engine, focus=focus)
     class_id = np.array([int(c) for c in batch["class_id"]], dtype=np.int64)
     out["class_id"] = _upload(class_id, image_set.device)
     diagnostics = {k: out.pop(k) for k in [k for k in out if k.startswith("_")]}

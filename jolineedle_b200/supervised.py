@@ -24,4 +24,5 @@ class TrajectoryMixin:
             batch, cfg.patch_size, cfg.max_seq_len, cfg.min_keypoints, cfg.max_keypoints,
             binomial_keypoints=cfg.binomial_keypoints, position=position,
             normalize=getattr(cfg, "normalize_on_gather", False), device=getattr(self, "device", None),
+            focus=getattr(cfg, "focus_layout", False),
         )

@@ -231,3 +231,37 @@ def test_incremental_sample_api_matches_oracle():
         for k in ("patches", "current_actions", "next_actions", "positions", "masks", "labels", "local_bboxes",
                   "patches_yolox", "bboxes_yolox"):
             assert sample[k].dtype == o_sample[k].dtype and torch.equal(sample[k].cpu(), o_sample[k]), (name, k)
+
+
+@pytest.mark.parametrize("host_images", [False, True])
+def test_batched_trajectories_in_focus_layout(host_images):
+    """``focus=True``: the trajectory glimpses and the detection patches leave the gather in the YOLOX Focus
+    space-to-depth layout; everything else is unchanged.  Also with pinned host images (tiles reused inside HBM
+    are copied in that layout)."""
+    from helpers import focus_restatement
+    from jolineedle_b200.env.simple_env import generate_trajectories
+
+    P, T, b = 32, 8, 6
+    rng = np.random.default_rng(15)
+    u8 = [torch.from_numpy(synth_u8(1, 3, 4 * P, 5 * P, salt=60 + i)[0]) for i in range(b)]
+    boxes = []
+    for i in range(b):
+        raw = []
+        for _ in range(int(rng.integers(0, 3))):
+            bw, bh = (int(v) for v in rng.integers(4, 2 * P, size=2))
+            x1, y1 = int(rng.integers(0, 5 * P - 4)), int(rng.integers(0, 4 * P - 4))
+            raw.append((x1, y1, min(x1 + bw, 5 * P - 1), min(y1 + bh, 4 * P - 1)))
+        boxes.append(bboxes_of(raw))
+    images = [t.pin_memory() for t in u8] if host_images else [t.cuda() for t in u8]
+    kw = dict(binomial_keypoints=True, seeds=list(range(40, 40 + b)), normalize=True, device="cuda", check=True)
+    random.seed(2)
+    plain = generate_trajectories({"image": images, "bboxes": boxes, "class_id": [0] * b}, P, T, 0, 3, **kw)
+    random.seed(2)
+    focus = generate_trajectories({"image": images, "bboxes": boxes, "class_id": [0] * b}, P, T, 0, 3, focus=True, **kw)
+    assert set(plain) == set(focus)
+    for k in plain:
+        if k in ("patches", "patches_yolox"):
+            assert tuple(focus[k].shape[-3:]) == (12, P // 2, P // 2)
+            assert torch.equal(focus[k], focus_restatement(plain[k])), k
+        else:
+            assert torch.equal(focus[k], plain[k]), k
