@@ -39,21 +39,29 @@ from ..gather import ImageSet
 from .common import Action, ACTION_DELTAS, DELTA_TABLE  # noqa: F401  (re-exported like the reference module)
 
 
+_GYM = None  # gymnasium module, False once an import has failed (a failed import walks sys.path every time)
+
+
 def _spaces(batch_size: int, channels: int, patch: int, rows: int, cols: int):
     """``observation_space`` / ``action_space`` as the reference declares them (general_env.py:61-72): gymnasium
     objects when that package is installed, plain descriptions with the same fields otherwise (no caller of the
     reference reads them; the env does not depend on gymnasium)."""
+    global _GYM
+    if _GYM is None:
+        try:
+            import gymnasium
+
+            _GYM = gymnasium
+        except Exception:
+            _GYM = False
     shape = (batch_size, channels, patch, patch)
-    try:
-        import gymnasium as gym
+    if _GYM:
+        return (_GYM.spaces.Box(low=0, high=1, shape=shape),
+                _GYM.spaces.Tuple((_GYM.spaces.Discrete(rows), _GYM.spaces.Discrete(cols))))
+    from types import SimpleNamespace
 
-        return (gym.spaces.Box(low=0, high=1, shape=shape),
-                gym.spaces.Tuple((gym.spaces.Discrete(rows), gym.spaces.Discrete(cols))))
-    except Exception:
-        from types import SimpleNamespace
-
-        return (SimpleNamespace(low=0, high=1, shape=shape),
-                SimpleNamespace(spaces=(SimpleNamespace(n=rows), SimpleNamespace(n=cols))))
+    return (SimpleNamespace(low=0, high=1, shape=shape),
+            SimpleNamespace(spaces=(SimpleNamespace(n=rows), SimpleNamespace(n=cols))))
 
 
 class NeedleGeneralEnv:
