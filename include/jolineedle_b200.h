@@ -290,18 +290,20 @@ int jn_visit_sources(const int64_t* positions, int32_t* first_slot, int n, int r
 
 /* ------------------------------------------------------------------------------------------
  * Glimpse pyramid: one level of NeedleGeneralEnv.init_glimps_images (general_env.py:84-115) --
- * TF.pad(level, [P]*4, "reflect") followed by TF.resize(.., [H, W], antialias=True) -- for float32 images.
- * src: n_images images of [C, H, W] floats, src_image_stride_bytes apart; dst likewise; tmp: n_images*C*H*W
- * floats of scratch.  first / count / weights ([size, k] float32) per axis are the antialiased bilinear filter
- * taps of every output index over the PADDED axis (size + 2*pad -> size), computed by the host exactly as ATen
- * does (jolineedle_b200/pyramid.py:aa_weights).  Rows pass, then columns pass, every output pixel the chain
- * t = s0*w0, t = fma(s_j, w_j, t): bit-identical to torch's CPU kernel (AVX2 / AVX-512 builds).
+ * TF.pad(level, [P]*4, "reflect") followed by TF.resize(.., [H, W], antialias=True) -- for float32 or uint8
+ * images (`dtype`, jn_dtype).  src: n_images images of [C, H, W] pixels, src_image_stride_bytes apart; dst
+ * likewise; tmp: n_images*C*H*W floats of scratch.  first / count / weights ([size, k] float32) per axis are the
+ * antialiased bilinear filter taps of every output index over the PADDED axis (size + 2*pad -> size), computed
+ * by the host exactly as ATen does (jolineedle_b200/pyramid.py:aa_weights).  Rows pass, then columns pass, every
+ * output pixel the chain t = s0*w0, t = fma(s_j, w_j, t): bit-identical to torch's CPU kernel (AVX2 / AVX-512
+ * builds).  uint8: torchvision casts to float32, resizes and casts back through torch.round (half to even); so
+ * does this.
  * ------------------------------------------------------------------------------------------ */
-int jn_resize_aa_reflect(const float* src, int64_t src_image_stride_bytes, float* tmp, float* dst,
-                         int64_t dst_image_stride_bytes, int n_images, int channels, int height, int width,
-                         int pad, const int32_t* first_x, const int32_t* count_x, const float* weights_x,
-                         int k_x, const int32_t* first_y, const int32_t* count_y, const float* weights_y,
-                         int k_y, void* stream);
+int jn_resize_aa_reflect(const void* src, int64_t src_image_stride_bytes, float* tmp, void* dst,
+                         int64_t dst_image_stride_bytes, int dtype /*jn_dtype*/, int n_images, int channels,
+                         int height, int width, int pad, const int32_t* first_x, const int32_t* count_x,
+                         const float* weights_x, int k_x, const int32_t* first_y, const int32_t* count_y,
+                         const float* weights_y, int k_y, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3  segmented scans.

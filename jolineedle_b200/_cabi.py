@@ -65,8 +65,8 @@ SIGNATURES = {
     "jn_patch_bitmaps": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, _P]),
     "jn_patch_bitmaps_f64": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, _P]),
     "jn_local_boxes_f64": (c_int, [_P, _P, c_int, c_int, _P, _P, c_int, _P, _P]),
-    "jn_resize_aa_reflect": (c_int, [_P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int,
-                                     _P, _P, _P, c_int, _P]),
+    "jn_resize_aa_reflect": (c_int, [_P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P,
+                                     c_int, _P, _P, _P, c_int, _P]),
     "jn_bitmap_unpack": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "jn_split_boxes": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "jn_local_boxes": (c_int, [_P, _P, c_int, c_int, _P, _P, c_int, _P, _P]),

@@ -1035,29 +1035,42 @@ int jn_env_props(const uint32_t* visited, const uint32_t* bbox, const uint8_t* h
 // ------------------------------------------------------------------------------------------
 // glimpse pyramid
 // ------------------------------------------------------------------------------------------
-int jn_resize_aa_reflect(const float* src, int64_t src_image_stride_bytes, float* tmp, float* dst,
-                         int64_t dst_image_stride_bytes, int n_images, int channels, int height, int width, int pad,
-                         const int32_t* first_x, const int32_t* count_x, const float* weights_x, int k_x,
+int jn_resize_aa_reflect(const void* src, int64_t src_image_stride_bytes, float* tmp, void* dst,
+                         int64_t dst_image_stride_bytes, int dtype, int n_images, int channels, int height, int width,
+                         int pad, const int32_t* first_x, const int32_t* count_x, const float* weights_x, int k_x,
                          const int32_t* first_y, const int32_t* count_y, const float* weights_y, int k_y,
                          void* stream) {
+  JN_REQUIRE(dtype == JN_U8 || dtype == JN_F32, "jn_resize_aa_reflect: dtype must be JN_U8 or JN_F32");
   JN_REQUIRE(n_images >= 0 && channels >= 1 && height >= 2 && width >= 2, "jn_resize_aa_reflect: bad sizes");
   JN_REQUIRE(pad >= 0 && pad < height && pad < width, "jn_resize_aa_reflect: reflect padding needs pad < image size");
   if (n_images == 0) return JN_OK;
   JN_REQUIRE(src && tmp && dst && first_x && count_x && weights_x && first_y && count_y && weights_y && k_x >= 1 &&
                  k_y >= 1,
              "jn_resize_aa_reflect: NULL pointer");
-  JN_REQUIRE(src_image_stride_bytes % 4 == 0 && dst_image_stride_bytes % 4 == 0, "jn_resize_aa_reflect: odd stride");
+  const int elem = dtype == JN_F32 ? 4 : 1;
+  JN_REQUIRE(src_image_stride_bytes % elem == 0 && dst_image_stride_bytes % elem == 0, "jn_resize_aa_reflect: odd stride");
   DeviceInfo dev;
   if (int rc = current_device_info(dev)) return rc;
   const long long total = (long long)n_images * channels * height * width;
   const dim3 grid(grid_for(total, 256 * 4, dev.sm_count * 16)), block(256);
-  jnk::resize_aa_rows_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, src_image_stride_bytes / 4, tmp, n_images,
-                                                                      channels, height, width, pad, first_x, count_x,
-                                                                      weights_x, k_x);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == JN_F32)
+    jnk::resize_aa_rows_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(src), src_image_stride_bytes / 4,
+                                                             tmp, n_images, channels, height, width, pad, first_x,
+                                                             count_x, weights_x, k_x);
+  else
+    jnk::resize_aa_rows_kernel<uint8_t><<<grid, block, 0, st>>>(static_cast<const uint8_t*>(src), src_image_stride_bytes,
+                                                               tmp, n_images, channels, height, width, pad, first_x,
+                                                               count_x, weights_x, k_x);
   JN_LAUNCHED();
-  jnk::resize_aa_cols_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(tmp, dst, dst_image_stride_bytes / 4, n_images,
-                                                                      channels, height, width, pad, first_y, count_y,
-                                                                      weights_y, k_y);
+  if (dtype == JN_F32)
+    jnk::resize_aa_cols_kernel<float><<<grid, block, 0, st>>>(tmp, static_cast<float*>(dst), dst_image_stride_bytes / 4,
+                                                             n_images, channels, height, width, pad, first_y, count_y,
+                                                             weights_y, k_y);
+  else
+    jnk::resize_aa_cols_kernel<uint8_t><<<grid, block, 0, st>>>(tmp, static_cast<uint8_t*>(dst), dst_image_stride_bytes,
+                                                               n_images, channels, height, width, pad, first_y, count_y,
+                                                               weights_y, k_y);
   JN_LAUNCHED();
   return JN_OK;
 }

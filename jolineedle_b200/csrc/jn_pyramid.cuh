@@ -8,6 +8,9 @@
 // host computed operation by operation like ATen (jolineedle_b200/pyramid.py:aa_weights), so a level equals the
 // reference's bit for bit.  The reflect padding is never materialised: padded index i maps to source index
 // reflect(i - pad).  Construction-time work (once per env), one thread per output pixel.
+//
+// uint8 images: torchvision casts them to float32, resizes, and casts back through torch.round (half to even) --
+// so the rows pass reads bytes as floats and the columns pass ends in a round-to-nearest-even conversion.
 #pragma once
 
 #include "jn_device.cuh"
@@ -19,8 +22,16 @@ __device__ __forceinline__ int reflect_index(int i, int n) {  // torch 'reflect'
   return i >= n ? 2 * (n - 1) - i : i;
 }
 
-// tmp[b, c, y, xo] from src[b, c, y, :]  (src images `src_image_stride` floats apart, [C, H, W] inside)
-__global__ void resize_aa_rows_kernel(const float* __restrict__ src, long long src_image_stride, float* __restrict__ tmp,
+__device__ __forceinline__ float pixel_as_float(float v) { return v; }
+__device__ __forceinline__ float pixel_as_float(uint8_t v) { return (float)v; }
+__device__ __forceinline__ void store_pixel(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_pixel(uint8_t* p, float v) {  // torch.round, then the cast
+  *p = (uint8_t)imin(imax(__float2int_rn(v), 0), 255);
+}
+
+// tmp[b, c, y, xo] from src[b, c, y, :]  (src images `src_image_stride` ELEMENTS apart, [C, H, W] inside)
+template <typename T>
+__global__ void resize_aa_rows_kernel(const T* __restrict__ src, long long src_image_stride, float* __restrict__ tmp,
                                       int B, int C, int H, int W, int pad, const int32_t* __restrict__ first,
                                       const int32_t* __restrict__ count, const float* __restrict__ wts, int k) {
   const long long total = (long long)B * C * H * W;
@@ -31,17 +42,18 @@ __global__ void resize_aa_rows_kernel(const float* __restrict__ src, long long s
     const int y = (int)(r % H); r /= H;
     const int c = (int)(r % C);
     const int b = (int)(r / C);
-    const float* row = src + b * src_image_stride + ((long long)c * H + y) * W;
+    const T* row = src + b * src_image_stride + ((long long)c * H + y) * W;
     const float* w = wts + (long long)xo * k;
     const int x0 = first[xo] - pad, n = count[xo];
-    float t = __fmul_rn(row[reflect_index(x0, W)], w[0]);
-    for (int j = 1; j < n; ++j) t = __fmaf_rn(row[reflect_index(x0 + j, W)], w[j], t);
+    float t = __fmul_rn(pixel_as_float(row[reflect_index(x0, W)]), w[0]);
+    for (int j = 1; j < n; ++j) t = __fmaf_rn(pixel_as_float(row[reflect_index(x0 + j, W)]), w[j], t);
     tmp[i] = t;
   }
 }
 
-// dst[b, c, yo, x] from tmp[b, c, :, x]  (tmp contiguous [B, C, H, W]; dst images `dst_image_stride` floats apart)
-__global__ void resize_aa_cols_kernel(const float* __restrict__ tmp, float* __restrict__ dst, long long dst_image_stride,
+// dst[b, c, yo, x] from tmp[b, c, :, x]  (tmp contiguous [B, C, H, W]; dst images `dst_image_stride` ELEMENTS apart)
+template <typename T>
+__global__ void resize_aa_cols_kernel(const float* __restrict__ tmp, T* __restrict__ dst, long long dst_image_stride,
                                       int B, int C, int H, int W, int pad, const int32_t* __restrict__ first,
                                       const int32_t* __restrict__ count, const float* __restrict__ wts, int k) {
   const long long total = (long long)B * C * H * W;
@@ -57,7 +69,7 @@ __global__ void resize_aa_cols_kernel(const float* __restrict__ tmp, float* __re
     const int y0 = first[yo] - pad, n = count[yo];
     float t = __fmul_rn(plane[(long long)reflect_index(y0, H) * W], w[0]);
     for (int j = 1; j < n; ++j) t = __fmaf_rn(plane[(long long)reflect_index(y0 + j, H) * W], w[j], t);
-    dst[b * dst_image_stride + ((long long)c * H + yo) * W + x] = t;
+    store_pixel(dst + b * dst_image_stride + ((long long)c * H + yo) * W + x, t);
   }
 }
 

@@ -87,8 +87,8 @@ class NeedleGeneralEnv:
         assert images.shape[0] == bboxes.shape[0]
         assert len(images.shape) == 4
         assert n_glimps_levels > 0
-        if n_glimps_levels != 1 and (translate is not None or images.dtype != torch.float32):
-            raise NotImplementedError("the glimpse pyramid (n_glimps_levels > 1) needs float32 images and no translate")
+        if n_glimps_levels != 1 and translate is not None:
+            raise NotImplementedError("the glimpse pyramid (n_glimps_levels > 1) does not combine with translate")
         # zero_copy: pinned HOST images are not uploaded -- every step's gather reads the glimpsed tiles in place
         # over PCIe, and with history=True a patch an episode has already seen is copied from the crop history in
         # HBM instead (jn_visit_sources), so each patch crosses PCIe at most once per episode
@@ -343,8 +343,9 @@ class NeedleGeneralEnv:
             out = torch.empty((self.batch_size, g) + self._set.out_shape(1, self._focus)[1:],
                               dtype=self._set.out_dtype(self._normalize), device=self.device)
         for level in range(g):
-            self._set.gather(self.positions, src_index=self._level_src[level], out=out[:, level], focus=self._focus,
-                             engine=self._engine, status=self._status, tag="step")
+            self._set.gather(self.positions, src_index=self._level_src[level], out=out[:, level],
+                             normalize=self._normalize, focus=self._focus, engine=self._engine, status=self._status,
+                             tag="step")
         return out
 
     @property

@@ -7,7 +7,8 @@ chain ``t = s0 * w0; t = fma(s_j, w_j, t)`` (its AVX2 / AVX-512 builds contract 
 every x86-64 server dispatches to).  :func:`aa_weights` restates the weight computation operation by operation,
 ``jn_resize_aa_reflect`` (csrc/jn_pyramid.cuh) runs the two passes with ``fmaf`` in the same order and folds the
 reflect padding into its index arithmetic, so the levels equal the reference's bit for bit
-(tests/test_glimpse_levels_gpu.py against a fixture of the unmodified reference).
+(tests/test_glimpse_levels_gpu.py against a fixture of the unmodified reference).  uint8 images take the route
+torchvision gives them: cast to float32, the same resize, ``torch.round`` (half to even), cast back.
 """
 from typing import Tuple
 
@@ -50,16 +51,17 @@ def aa_weights(in_size: int, out_size: int) -> Tuple[np.ndarray, np.ndarray, np.
 
 
 def build_levels(images: torch.Tensor, patch_size: int, n_levels: int) -> torch.Tensor:
-    """``[B, n_levels, C, H, W]`` stack of progressively zoomed-out copies of float32 CUDA ``images [B, C, H, W]``
-    (level 0 = the input)."""
+    """``[B, n_levels, C, H, W]`` stack of progressively zoomed-out copies of float32 or uint8 CUDA
+    ``images [B, C, H, W]`` (level 0 = the input).  uint8 levels are what torchvision makes of uint8 tensors: the
+    float32 resize of the bytes, rounded half to even, level after level."""
     _cabi.require_cuda(images, "images")
-    if images.dtype != torch.float32:
-        raise NotImplementedError("the glimpse pyramid is built from float32 images")
+    code = _cabi.dtype_code(images.dtype)
+    elem = images.element_size()
     b, c, h, w = images.shape
     if patch_size >= h or patch_size >= w:
         raise ValueError("reflect padding needs patch_size < image size")
     dev = images.device
-    out = torch.empty((b, n_levels, c, h, w), dtype=torch.float32, device=dev)
+    out = torch.empty((b, n_levels, c, h, w), dtype=images.dtype, device=dev)
     out[:, 0] = images
     if n_levels == 1:
         return out
@@ -75,7 +77,7 @@ def build_levels(images: torch.Tensor, patch_size: int, n_levels: int) -> torch.
         for level in range(1, n_levels):
             src, dst = out[:, level - 1], out[:, level]
             _cabi.check(lib.jn_resize_aa_reflect(
-                src.data_ptr(), src.stride(0) * 4, tmp.data_ptr(), dst.data_ptr(), dst.stride(0) * 4, b, c, h, w,
+                src.data_ptr(), src.stride(0) * elem, tmp.data_ptr(), dst.data_ptr(), dst.stride(0) * elem, code, b, c, h, w,
                 patch_size, fx.data_ptr(), cx.data_ptr(), wx.data_ptr(), kx, fy.data_ptr(), cy.data_ptr(),
                 wy.data_ptr(), ky, _cabi.stream_ptr(dev)))
     return out

@@ -38,15 +38,41 @@ def test_glimpse_pyramid_matches_reference(name, history):
     env.check_status()
 
 
+def test_uint8_glimpse_pyramid_matches_reference():
+    """uint8 images (the dtype the reference's docstring names, general_env.py:28): torchvision resizes them
+    through float32 + torch.round, level after level; plain uint8 crops and normalised ones."""
+    from jolineedle_b200.env.general_env import NeedleGeneralEnv
+
+    c = scenario(load_golden("glimpse_levels.npz"), "lv3u8")
+    levels = int(c["levels"])
+    table = torch.from_numpy(load_golden("norm.npz")["u8_over_255"])
+    for normalize in (False, True):
+        env = NeedleGeneralEnv(torch.from_numpy(c["u8"]).cuda(), torch.from_numpy(c["boxes"]), 16, 6, levels, True,
+                               normalize=normalize)
+        assert env.images.dtype == torch.uint8 and np.array_equal(env.images.cpu().numpy(), c["images"])
+        got = [env.reset(torch.from_numpy(c["start"]))[0]]
+        for t, a in enumerate(c["actions"]):
+            out = env.step(torch.from_numpy(a))
+            got.append(out[0])
+            assert np.array_equal(out[1].cpu().numpy(), c["rewards"][t])
+        for t, p in enumerate(got):
+            want = torch.from_numpy(c["patches"][t])
+            assert torch.equal(p.cpu(), table[want.long()] if normalize else want), (t, normalize)
+        env.check_status()
+
+
+@pytest.mark.parametrize("as_bytes", [False, True])
 @pytest.mark.parametrize("P,gh,gw,levels", [(32, 4, 5, 3), (448, 5, 6, 2), (64, 7, 3, 4)])
-def test_pyramid_levels_equal_torchvision_cpu(P, gh, gw, levels):
+def test_pyramid_levels_equal_torchvision_cpu(P, gh, gw, levels, as_bytes):
     """Other shapes (incl. the LARD geometry), straight against the reference's own calls on the CPU."""
     import torchvision.transforms.functional as TF
 
     from jolineedle_b200.pyramid import build_levels
 
     g = torch.Generator().manual_seed(P + levels)
-    images = torch.randint(0, 256, (2, 3, gh * P, gw * P), dtype=torch.uint8, generator=g).float() / 255
+    images = torch.randint(0, 256, (2, 3, gh * P, gw * P), dtype=torch.uint8, generator=g)
+    if not as_bytes:
+        images = images.float() / 255
     want, cur = [images], images
     for _ in range(levels - 1):  # general_env.py:95-111
         cur = TF.resize(TF.pad(cur, padding=[P] * 4, padding_mode="reflect"), size=[gh * P, gw * P], antialias=True)

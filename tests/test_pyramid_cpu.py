@@ -57,3 +57,20 @@ def test_filter_taps_are_normalised_and_inside_the_axis():
         sums = np.array([weights[i, :count[i]].astype(np.float64).sum() for i in range(size)])
         assert np.allclose(sums, 1.0, atol=1e-6)
         assert all((weights[i, count[i]:] == 0).all() for i in range(size))
+
+
+@pytest.mark.skipif(torch.backends.cpu.get_cpu_capability() not in ("AVX2", "AVX512"),
+                    reason="ATen's DEFAULT build does not contract multiply-adds")
+def test_uint8_levels_are_the_float_resize_rounded_half_to_even():
+    """torchvision's route for uint8 tensors (cast to float32, resize, torch.round, cast back) -- what the uint8
+    mode of jn_resize_aa_reflect follows -- level after level."""
+    import torchvision.transforms.functional as TF
+
+    P, h, w = 16, 80, 96
+    g = torch.Generator().manual_seed(3)
+    cur = torch.randint(0, 256, (2, 3, h, w), dtype=torch.uint8, generator=g)
+    mine = cur.numpy()
+    for _ in range(3):
+        cur = TF.resize(TF.pad(cur, padding=[P] * 4, padding_mode="reflect"), size=[h, w], antialias=True)
+        mine = np.rint(level_restated(mine.astype(np.float32), P)).astype(np.uint8)
+        assert cur.dtype == torch.uint8 and np.array_equal(mine, cur.numpy())
