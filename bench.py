@@ -533,17 +533,20 @@ def run_workload(wl_name, args, ctx, primary):
     barrier()
     t_begin = time.perf_counter()
     ev0.record()
-    step_host = [time.perf_counter()]
+    step_host, step_cpu = [time.perf_counter()], [time.thread_time()]
     for s in range(args.steps):
         out = wl.run(args.warmup + s)
         g = wl.gaze_steps(out)
         units += g
         valid.append(g)
         step_host.append(time.perf_counter())
+        step_cpu.append(time.thread_time())
     ev1.record()
     barrier()
     t_end = time.perf_counter()
     host_ms = [round(1e3 * (b - a), 2) for a, b in zip(step_host, step_host[1:])]
+    # CPU time of the launching thread per step: well below host_ms = the thread was waiting (driver, queue), not working
+    host_cpu_ms = [round(1e3 * (b - a), 2) for a, b in zip(step_cpu, step_cpu[1:])]
     launches = _cabi.launch_count() - launches0
     timing, gather.TIMING = gather.TIMING.records, None
     ms = max_over_ranks(ev0.elapsed_time(ev1), device)
@@ -580,7 +583,8 @@ def run_workload(wl_name, args, ctx, primary):
         roofline["kernel_ms_ncu"] = round(ncu_s * 1e3, 4)
         roofline["frac_kernel_ncu"] = round(sum(byts) / len(byts) / ncu_s / 1e9 / peak, 4)
     result = {"value": value, "ms_per_step": ms / args.steps, "roofline": roofline, "gpu_launches": launches,
-              "host_ms_per_step": host_ms, "gather_ms_by_tag": gather_ms, "gather_items_by_tag": gather_items,
+              "host_ms_per_step": host_ms, "host_cpu_ms_per_step": host_cpu_ms, "gather_ms_by_tag": gather_ms,
+              "gather_items_by_tag": gather_items,
               "clocks": clocks.summary(t_begin, t_end) if rank == 0 else None}
     if fused:  # host time of one env step (python + one native call), the launch-bound regime of small batches
         result["host_us_per_env_step"] = round(1e3 * statistics.median(host_ms) / (wl.T + 1), 1)

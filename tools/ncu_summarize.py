@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Reduce `ncu --set full` reports to the handful of numbers the docs and bench.py quote.
 
-    python tools/ncu_summarize.py NAME=report.ncu-rep [NAME=report.ncu-rep ...] --out profiles/r01/ncu_summary.json
+    python tools/ncu_summarize.py NAME=report.ncu-rep [NAME=report.ncu-rep ...] --out profiles/r02/ncu_summary.json --source-hash $(cat gpurun_out/<tag>/source_hash.txt)
 
 For every kernel launch in a report: duration, DRAM bytes read / written (their sum is the `traffic`
 of bench.py's roofline object), DRAM throughput as a fraction of ncu's own peak, threads per executed
