@@ -365,7 +365,7 @@ class NeedleGeneralEnv:
         a.out = None if out is None else out.data_ptr()
         timing = _gather_mod.TIMING
         with _cabi.on_device(self.device):
-            pair = timing.begin() if (timing is not None and out is not None) else None
+            pair = timing.begin(self.device) if (timing is not None and out is not None) else None
             rc = fn(self._set_handle, self._hist_handle, self._args_ref, _cabi.stream_ptr(self.device))
             if pair is not None:
                 timing.end(pair, "step", self.batch_size)

@@ -23,15 +23,19 @@ class LaunchTimer:
                      for _ in range(capacity)]
         self.records: list = []
 
-    def begin(self):
+    def begin(self, device=None):
         k = len(self.records)
         pair = self.pool[k] if k < len(self.pool) else (torch.cuda.Event(enable_timing=True),
                                                         torch.cuda.Event(enable_timing=True))
-        pair[0].record()
-        return pair
+        # (Event.record() without a stream looks the current stream up through several python layers, ~13 us;
+        # the cached Stream object of the raw handle costs a dict lookup)
+        stream = None if device is None else _stream_object(device, _cabi.stream_ptr(device))
+        pair[0].record(stream) if stream is not None else pair[0].record()
+        return pair, stream
 
-    def end(self, pair, tag: str, n_items: int):
-        pair[1].record()
+    def end(self, token, tag: str, n_items: int):
+        pair, stream = token
+        pair[1].record(stream) if stream is not None else pair[1].record()
         self.records.append((tag, n_items, pair[0], pair[1]))
 
 
@@ -185,7 +189,7 @@ class ImageSet:
             stride = (out.stride(0) if n > 1 else out[0].numel()) * out.element_size()
             timing = TIMING
             with _cabi.on_device(device):
-                pair = timing.begin() if timing is not None else None
+                pair = timing.begin(device) if timing is not None else None
                 rc = lib.jn_gather(handle, positions.data_ptr(), None, p_shifts, n, out.data_ptr(), stride, flags, code,
                                    p_status, _cabi.stream_ptr(device))
                 if pair is not None:
@@ -250,7 +254,7 @@ class ImageSet:
         self._order_after_table()
         timing = TIMING
         with _cabi.on_device(self.device):
-            pair = timing.begin() if timing is not None else None
+            pair = timing.begin(self.device) if timing is not None else None
             rc = _cabi.lib().jn_gather(
                 self._handle, _cabi.ptr(positions), _cabi.ptr(src_index), _cabi.ptr(shifts), n, out.data_ptr(), stride,
                 flags,
