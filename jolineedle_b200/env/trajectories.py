@@ -517,20 +517,33 @@ def generate_trajectories(
     """Batched supervised trajectories (``SupervisedTrainer.generate_trajectories``,
     supervised.py:95-136): ``batch`` holds lists ``image`` ([C,H,W] tensors), ``bboxes`` (lists
     of ``BBox``) and ``class_id``.  Returns the collated dict of the reference on the GPU.
+    ``image`` may also be ONE stacked ``[B, C, H, W]`` tensor when the images share a size.
     ``seeds`` (one per image) makes the plans reproducible; the reference builds unseeded envs.
     CPU images are uploaded to ``device`` first (there is no CPU path).  ``check`` synchronises and raises if
     a kernel flagged its input (a position outside the grid, a plan the expansion could not follow); without it
     the flags travel in ``stats["status"]`` and nothing waits for the device.  ``focus``: ``patches`` and
     ``patches_yolox`` come out in the YOLOX Focus space-to-depth layout ``[4C, P/2, P/2]`` (what the detector's
     stem computes first), written that way by the gather itself."""
-    images: List[torch.Tensor] = list(batch["image"])
-    if device is not None:
-        # Pinned host images are NOT uploaded: a supervised episode looks at ~10 of an image's 30
-        # patches once, so the gather reads just those tiles over PCIe (zero-copy).  Pageable host
-        # images have to be staged through a full upload.
-        images = [im if (im.is_cuda or (zero_copy and im.is_pinned())) else im.to(device, non_blocking=True)
-                  for im in images]
-    plans = plan_batch(batch["bboxes"], [im.shape[1] for im in images], [im.shape[2] for im in images], patch_size,
+    stacked = batch["image"] if isinstance(batch["image"], torch.Tensor) else None
+    if stacked is not None:
+        # one [B, C, H, W] tensor (images of one size, e.g. what `pinned_u8_collate` makes of a LARD batch): a
+        # single slab -- no per-image bookkeeping on the host, tensor tiles instead of per-row copies
+        if stacked.dim() != 4:
+            raise ValueError("a stacked image batch must be [B, C, H, W]")
+        if device is not None and not (stacked.is_cuda or (zero_copy and stacked.is_pinned())):
+            stacked = stacked.to(device, non_blocking=True)
+        images = stacked
+        heights, widths = [stacked.shape[2]] * stacked.shape[0], [stacked.shape[3]] * stacked.shape[0]
+    else:
+        images: List[torch.Tensor] = list(batch["image"])
+        if device is not None:
+            # Pinned host images are NOT uploaded: a supervised episode looks at ~10 of an image's 30
+            # patches once, so the gather reads just those tiles over PCIe (zero-copy).  Pageable host
+            # images have to be staged through a full upload.
+            images = [im if (im.is_cuda or (zero_copy and im.is_pinned())) else im.to(device, non_blocking=True)
+                      for im in images]
+        heights, widths = [im.shape[1] for im in images], [im.shape[2] for im in images]
+    plans = plan_batch(batch["bboxes"], heights, widths, patch_size,
                        min_keypoints, max_keypoints, binomial_keypoints, position, seeds, planner, deferred=True)
     try:
         image_set = ImageSet(images, patch_size, device=device)  # while the native planner runs on its own thread

@@ -265,3 +265,31 @@ def test_batched_trajectories_in_focus_layout(host_images):
             assert torch.equal(focus[k], focus_restatement(plain[k])), k
         else:
             assert torch.equal(focus[k], plain[k]), k
+
+
+@pytest.mark.parametrize("where", ["cuda", "pinned"])
+def test_stacked_image_batch_equals_the_list_of_images(where):
+    """``batch["image"]`` as one [B, C, H, W] tensor (same-size images, e.g. a `pinned_u8_collate` batch): same
+    result as the list the reference's DataLoader yields, on the device and read in place from pinned memory."""
+    from jolineedle_b200.env.simple_env import generate_trajectories
+
+    P, T, b = 32, 8, 5
+    rng = np.random.default_rng(8)
+    u8 = torch.from_numpy(synth_u8(b, 3, 4 * P, 6 * P, salt=70))
+    boxes = []
+    for i in range(b):
+        raw = []
+        for _ in range(int(rng.integers(0, 3))):
+            bw, bh = (int(v) for v in rng.integers(4, 2 * P, size=2))
+            x1, y1 = int(rng.integers(0, 6 * P - 4)), int(rng.integers(0, 4 * P - 4))
+            raw.append((x1, y1, min(x1 + bw, 6 * P - 1), min(y1 + bh, 4 * P - 1)))
+        boxes.append(bboxes_of(raw))
+    stacked = u8.cuda() if where == "cuda" else u8.pin_memory()
+    kw = dict(binomial_keypoints=True, seeds=list(range(b)), normalize=True, device="cuda", check=True)
+    random.seed(4)
+    a = generate_trajectories({"image": [stacked[i] for i in range(b)], "bboxes": boxes, "class_id": [1] * b}, P, T, 0, 3, **kw)
+    random.seed(4)
+    c = generate_trajectories({"image": stacked, "bboxes": boxes, "class_id": [1] * b}, P, T, 0, 3, **kw)
+    assert set(a) == set(c)
+    for k in a:
+        assert torch.equal(a[k], c[k]), k
