@@ -607,6 +607,16 @@ int gather_launch(const jn_images* set, const GatherRequest& rq, cudaStream_t st
   const int shift_pitch = P * set->elem + 16;
   const bool shift_xform_ok = set->tensor_ok && set->n_slabs == 1 && shift_pitch / 8 <= 256 && P >= 8 &&
                               (normalize || set->dtype == JN_F32);
+  // Plain float32 copies of resident single-slab sets with tiles of 256 pixels or more: the converting kernel's
+  // float32 pass-through mode (tickets, tensor tiles) instead of the pure-DMA copy kernel with its static round
+  // robin -- 1.03 / 1.04 / 1.06 of the measured copy peak at P = 256 / 448 / 1024 against 1.00 / 1.00 / 0.99
+  // (profiles/r02/f32_plain_routes.jsonl); smaller tiles stay on the copy kernel (0.92 vs 0.82 at P = 128).
+  // JN_F32_PLAIN=copy restores the old route (A/B).  Only under `auto`: an explicit engine means the copy kernel.
+  static const bool f32_plain_copy_only = [] { const char* e = getenv("JN_F32_PLAIN"); return e && e[0] == 'c'; }();
+  const bool f32_via_xform = engine == JN_ENGINE_AUTO && !f32_plain_copy_only && plain_copy && set->dtype == JN_F32 &&
+                             P >= 256 && out_aligned && set->tensor_ok && set->n_slabs == 1 && !set->host_mapped &&
+                             !shifts && !set->padded;
+  if (f32_via_xform) engine = JN_ENGINE_TENSOR;
   if (engine == JN_ENGINE_AUTO) {
     if (!tma_mode || !out_aligned || !set->bulk_ok) engine = JN_ENGINE_LDG;
     else if (shifts || set->padded) engine = (shift_copy_ok || shift_xform_ok) ? JN_ENGINE_TENSOR : JN_ENGINE_LDG;
@@ -653,7 +663,7 @@ int gather_launch(const jn_images* set, const GatherRequest& rq, cudaStream_t st
   }
 
   // TMA engines: chunk geometry
-  const bool use_copy = plain_copy && !shift_xform;
+  const bool use_copy = plain_copy && !shift_xform && !f32_via_xform;
   const GatherTune tune = gather_tune(P, set->elem, use_copy, focus, engine);
   const int target = use_copy ? tune.copy_chunk : tune.xform_chunk;
   const int rows = pick_rows(P, set->elem, target, focus);
