@@ -325,3 +325,31 @@ def test_native_planner_self_check_and_fallback(monkeypatch):
     b = tr.plan_batch(boxes, [128], [160], 32, 0, 3, True, None, [5], planner="native")
     for k in ("start", "seg_begin", "seg_to", "seg_tgt", "seg_flags", "draw_begin", "draws", "det_begin", "det_yx"):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
+
+
+def test_boxes_array_flattening_and_exactness_flag():
+    """Host packing of the trainer's lists of BBox: x1, y1, x2, y2 order, zero-padded rows, per-image counts, and
+    the flag that sends boxes with fractional coordinates to the float64 kernels / the python planner."""
+    from jolineedle_b200.env.trajectories import boxes_array
+
+    boxes = [[BBox(Position(2, 1), Position(8, 5)), BBox(Position(0, 0), Position(3, 3))], [],
+             [BBox(Position(7, 9), Position(20, 30))]]
+    arr, counts, n_max, exact, arr_f = boxes_array(boxes, want_float=True)
+    assert arr.dtype == np.int64 and arr.shape == (3, 2, 4) and counts.tolist() == [2, 0, 1] and n_max == 2
+    assert arr[0].tolist() == [[1, 2, 5, 8], [0, 0, 3, 3]] and arr[1].tolist() == [[0] * 4] * 2
+    assert arr[2].tolist() == [[9, 7, 30, 20], [0, 0, 0, 0]] and exact and arr_f is None
+    # whole-pixel floats are still exact; one fractional coordinate is not
+    whole = [[BBox(Position(2.0, 1.0), Position(8.0, 5.0))]]
+    assert boxes_array(whole, want_float=True)[3:] == (True, None)
+    frac = [[BBox(Position(2.5, 1), Position(8, 5))], [BBox(Position(1, 1), Position(4, 4))]]
+    arr, counts, n_max, exact, arr_f = boxes_array(frac, want_float=True)
+    assert not exact and arr_f.dtype == np.float64 and arr_f[0, 0].tolist() == [1.0, 2.5, 5.0, 8.0]
+    assert arr_f[1, 0].tolist() == [1.0, 1.0, 4.0, 4.0] and arr[0, 0].tolist() == [1, 2, 5, 8]  # (truncated copy)
+    # no boxes at all
+    arr, counts, n_max, exact = boxes_array([[], []])
+    assert arr.shape == (2, 1, 4) and counts.tolist() == [0, 0] and n_max == 0 and exact
+    # fractional boxes are planned by the python planner, whatever was asked for with "auto"
+    from jolineedle_b200.env.trajectories import plan_batch
+
+    p = plan_batch(frac, [64, 64], [64, 64], 16, 0, 2, True, None, [1, 2], planner="auto")
+    assert p.boxes_f64 is not None and p.boxes_f64.shape == (2, 1, 4)
