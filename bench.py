@@ -17,6 +17,7 @@ Under torchrun every rank owns one GPU and its own shard of episodes (weak scali
 the step time is the max over ranks, measured with CUDA events on the launch stream.
 """
 import argparse
+import gc
 import json
 import os
 import random
@@ -279,6 +280,7 @@ class ReinforceWorkload:
         self.batch, self.rank, self.device, self.src_dtype = batch, rank, device, src_dtype
         self.h, self.w = self.GRID[0] * self.PATCH, self.GRID[1] * self.PATCH
         self.launches_per_step = self.T + 1
+        self.host_split = []
         rng = np.random.default_rng(4321 + rank)
         raw = synth_boxes(rng, batch, self.h, self.w)
         nmax = max(len(r) for r in raw)
@@ -319,6 +321,7 @@ class ReinforceWorkload:
         from jolineedle_b200.reinforce import rollout_tail
 
         e2e = images is not None
+        c0 = time.perf_counter()
         env = NeedleGeneralEnv(self.images if not e2e else images, self.boxes_pinned if e2e else self.boxes_dev,
                                self.PATCH, self.T, 1, stop_enabled=True, normalize=(self.src_dtype == "u8"),
                                history=True, device=device, translate=self.translate_dev, zero_copy=e2e)
@@ -328,13 +331,21 @@ class ReinforceWorkload:
         self.gen.manual_seed(step * 31 + self.rank)
         # the policy's stand-in: one row of action codes per env step
         actions = torch.randint(0, 9, (self.T, self.batch), device=self.device, generator=self.gen).unbind(0)
+        c1 = time.perf_counter()
         env.reset()
+        c2 = time.perf_counter()
         for t in range(self.T):
             env.step(actions[t])
+        c3 = time.perf_counter()
         rewards_tn, terminated_tn, _ = env.rollout_buffers()  # [T, B] rings the steps wrote: nothing to stack
         out = rollout_tail(rewards_tn, terminated_tn)
         out["positions"] = env.positions
         out["host_tiles"] = env.host_tiles  # tiles read over PCIe (zero-copy env only)
+        del env
+        c4 = time.perf_counter()
+        # where the launching thread spends a rollout (diagnostic; ms): env construction + actions, reset, the T
+        # step calls, returns + teardown
+        self.host_split.append((c1 - c0, c2 - c1, c3 - c2, c4 - c3))
         return out
 
     def host_tiles(self, out, stats):
@@ -530,6 +541,9 @@ def run_workload(wl_name, args, ctx, primary):
     valid = []
     launches0 = _cabi.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if hasattr(wl, "host_split"):
+        wl.host_split.clear()
+    mem0, gc0 = torch.cuda.memory_stats(device), [g["collections"] for g in gc.get_stats()]
     barrier()
     t_begin = time.perf_counter()
     ev0.record()
@@ -548,6 +562,18 @@ def run_workload(wl_name, args, ctx, primary):
     # CPU time of the launching thread per step: well below host_ms = the thread was waiting (driver, queue), not working
     host_cpu_ms = [round(1e3 * (b - a), 2) for a, b in zip(step_cpu, step_cpu[1:])]
     launches = _cabi.launch_count() - launches0
+    mem1 = torch.cuda.memory_stats(device)
+    # host-side diagnostics of the timed region: cudaMalloc / cudaFree calls of the caching allocator, python GC
+    # passes per generation, and (RL workloads) the split of a rollout's host time
+    host_diag = {"device_allocs": mem1.get("num_device_alloc", 0) - mem0.get("num_device_alloc", 0),
+                 "device_frees": mem1.get("num_device_free", 0) - mem0.get("num_device_free", 0),
+                 "alloc_retries": mem1.get("num_alloc_retries", 0) - mem0.get("num_alloc_retries", 0),
+                 "gc_collections": [g["collections"] - g0 for g, g0 in zip(gc.get_stats(), gc0)]}
+    if getattr(wl, "host_split", None):
+        rows = wl.host_split
+        host_diag["rollout_split_ms"] = dict(zip(
+            ("construct", "reset", "steps", "tail"),
+            (round(1e3 * sum(r[i] for r in rows) / len(rows), 3) for i in range(4))))
     timing, gather.TIMING = gather.TIMING.records, None
     ms = max_over_ranks(ev0.elapsed_time(ev1), device)
     total_units = sum_over_ranks(float(units.item()), device)
@@ -584,7 +610,7 @@ def run_workload(wl_name, args, ctx, primary):
         roofline["frac_kernel_ncu"] = round(sum(byts) / len(byts) / ncu_s / 1e9 / peak, 4)
     result = {"value": value, "ms_per_step": ms / args.steps, "roofline": roofline, "gpu_launches": launches,
               "host_ms_per_step": host_ms, "host_cpu_ms_per_step": host_cpu_ms, "gather_ms_by_tag": gather_ms,
-              "gather_items_by_tag": gather_items,
+              "gather_items_by_tag": gather_items, "host_diag": host_diag,
               "clocks": clocks.summary(t_begin, t_end) if rank == 0 else None}
     if fused:  # host time of one env step (python + one native call), the launch-bound regime of small batches
         result["host_us_per_env_step"] = round(1e3 * statistics.median(host_ms) / (wl.T + 1), 1)

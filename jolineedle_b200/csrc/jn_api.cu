@@ -179,6 +179,24 @@ int pick_rows(int patch, int elem, int target_bytes, bool need_even) {
   return best;
 }
 
+// L2 promotion of the tensor maps: how far the L2 widens a TMA read beyond the bytes asked for.  Tile rows are
+// short (128 ... 448 bytes of uint8) and start anywhere on a 64-byte grid, so 256-byte promotion fetched 29-33 % more
+// from DRAM than the tiles hold (ncu: 0.79 GB read for 0.62 GB of cfg-3 tiles); 64 bytes reads what is asked for
+// (profiles/r02/sweep_l2_promotion.jsonl: uint8 P = 448 0.945 -> 0.991 of the HBM peak, float32 unchanged).
+// JN_TMA_L2_PROMOTION = none | 64 | 128 | 256 overrides the choice (A/B knob).
+CUtensorMapL2promotion l2_promotion(CUtensorMapL2promotion chosen) {
+  static const int forced = [] {
+    const char* e = std::getenv("JN_TMA_L2_PROMOTION");
+    if (!e || !*e) return -1;
+    if (!std::strcmp(e, "none")) return (int)CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    if (!std::strcmp(e, "64")) return (int)CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+    if (!std::strcmp(e, "128")) return (int)CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    if (!std::strcmp(e, "256")) return (int)CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    return -1;
+  }();
+  return forced < 0 ? chosen : (CUtensorMapL2promotion)forced;
+}
+
 int encode_slab_map(CUtensorMap* map, const void* ptr, int elem, int n_planes, int height, int width, int box_w,
                     int kbox, int rows, bool three_d = false) {
   EncodeTiledFn fn = encode_tiled_fn();
@@ -192,7 +210,7 @@ int encode_slab_map(CUtensorMap* map, const void* ptr, int elem, int n_planes, i
     cuuint32_t estr3[3] = {1, 1, 1};
     const CUtensorMapDataType dt3 = elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
     CUresult r3 = fn(map, dt3, 3, const_cast<void*>(ptr), dims3, strides3, box3, estr3, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_NONE, l2_promotion(CU_TENSOR_MAP_L2_PROMOTION_L2_64B), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r3 != CUDA_SUCCESS) return fail(JN_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r3);
     return JN_OK;
   }
@@ -203,7 +221,7 @@ int encode_slab_map(CUtensorMap* map, const void* ptr, int elem, int n_planes, i
   cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUtensorMapDataType dt = elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
   CUresult r = fn(map, dt, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_SWIZZLE_NONE, l2_promotion(CU_TENSOR_MAP_L2_PROMOTION_L2_64B), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(JN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (dims %llu x %llu x %llu x %llu, box %u x %u x %u)",
                 (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
@@ -225,8 +243,8 @@ int encode_shift_map(CUtensorMap* map, const void* ptr, int elem, int n_planes, 
   cuuint32_t box[3] = {(cuuint32_t)(pitch / 8), (cuuint32_t)rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  l2_promotion(CU_TENSOR_MAP_L2_PROMOTION_L2_64B), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(JN_ERR_CUDA, "cuTensorMapEncodeTiled (translated) failed with CUresult %d", (int)r);
   return JN_OK;
 }
@@ -587,6 +605,13 @@ int gather_launch(const jn_images* set, const GatherRequest& rq, cudaStream_t st
   a.padded = set->padded ? 1 : 0;
   a.actions = rq.actions; a.grid_rows = rq.grid_rows; a.grid_cols = rq.grid_cols;
   a.wait_prior = rq.wait_prior ? 1 : 0;
+  // Streaming stores (st.global.cs) for uint8 -> float32 launches whose crops are of the order of the L2 (<= 256 MB):
+  // +1.7 % on cfg 4 and +2 % on 256 tiles of 256^2; launches of GBs gain nothing or lose (cfg 2's trajectory
+  // gather -1.6 %), float32 pass-through -0.5 % (profiles/r02/sweep_l2_hint.jsonl, stream_stores_ab.jsonl).
+  // JN_STREAM_STORES = 0 / 1 forces.
+  static const int stream_stores = [] { const char* e = std::getenv("JN_STREAM_STORES"); return e && *e ? std::atoi(e) : -1; }();
+  a.stream_stores = stream_stores >= 0 ? stream_stores
+                    : (((rq.flags & JN_GATHER_NORMALIZE) && (long long)n_items * tile_out_bytes <= (256ll << 20)) ? 1 : 0);
 
   const bool plain_copy = !normalize && !focus;
   const bool out_aligned = reinterpret_cast<uintptr_t>(out) % 16 == 0 && out_item_stride_bytes % 16 == 0;
@@ -916,6 +941,10 @@ int launch_step(const jnk::StepArgs& a, cudaStream_t stream, bool pdl = false) {
   const dim3 grid(grid_for(a.n, 64, dev.sm_count * 16)), block(64);  // a warp steps 32 episodes
 #define JN_STEP(G) \
   case G: JN_CUDA(launch_kernel(jnk::env_step_kernel<G>, grid, block, 0, stream, pdl, a)); break;
+  if (a.words > 32) {  // its own instantiation: the second block of words costs 120 registers
+    JN_CUDA(launch_kernel(jnk::env_step_kernel<32, true>, grid, block, 0, stream, pdl, a));
+    return JN_OK;
+  }
   switch (g) { JN_STEP(1) JN_STEP(2) JN_STEP(4) JN_STEP(8) JN_STEP(16) JN_STEP(32) }
 #undef JN_STEP
   return JN_OK;

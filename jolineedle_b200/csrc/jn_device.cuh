@@ -171,5 +171,13 @@ __device__ __forceinline__ void st_f4(float* p, float a, float b, float c, float
 __device__ __forceinline__ void st_f2(float* p, float a, float b) {
   asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
+// streaming variants (evict-first in L2): the crops of a uint8 -> float32 gather are written once and are four
+// times the bytes read; used for launches whose crops are of the order of the L2 (jn_api.cu: stream_stores)
+__device__ __forceinline__ void st_f4_cs(float* p, float a, float b, float c, float d) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void st_f2_cs(float* p, float a, float b) {
+  asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
 
 }  // namespace jnk

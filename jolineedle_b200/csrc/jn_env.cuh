@@ -266,8 +266,9 @@ __global__ void env_reset_kernel(const StepArgs a) {
 //   phase C  lane = episode: reward = fl32(fl32(fresh + cost) + stop_eval), flags, counters; coalesced stores.
 //
 // One-word grids (5x6 LARD grid, G = 1) degenerate to a lane per episode; the 32x32 aerial grid (G = 32) to 32
-// warp-wide iterations.  Counts are 16-bit fields: grids of up to 65535 patches.
-template <int G>
+// warp-wide iterations; wider grids (kWide) keep a second block of 32 words in registers and loop over any
+// further ones.  Counts are 16-bit fields: grids of up to 65535 patches.
+template <int G, bool kWide = false>  // kWide: more than 32 bitmap words (G == 32)
 __global__ void __launch_bounds__(64) env_step_kernel(const __grid_constant__ StepArgs a) {
   pdl_launch_dependents();  // the gather that follows derives its positions from pos_in + actions itself
   constexpr int kPer = 32 / G;
@@ -308,6 +309,19 @@ __global__ void __launch_bounds__(64) env_step_kernel(const __grid_constant__ St
       vv[it] = ok ? a.visited[idx] : 0u;
       bb[it] = ok ? a.bbox[idx] : 0u;
     }
+    // grids of 1025 ... 2048 patches: the second block of 32 words, loaded up front as well (a block of two warps
+    // has registers to spare; loading them inside the loop below exposed one memory round trip per episode)
+    constexpr int kTail = kWide ? 32 : 1;
+    uint32_t tv[kTail], tb[kTail];
+    if (kWide) {
+#pragma unroll
+      for (int it = 0; it < kTail; ++it) {
+        const bool ok = base + it < a.n && sub + 32 < a.words;
+        const long long idx = (long long)(base + it) * a.words + sub + 32;
+        tv[it] = ok ? a.visited[idx] : 0u;
+        tb[it] = ok ? a.bbox[idx] : 0u;
+      }
+    }
     uint32_t mine_fe = 0, mine_mf = 0;  // found | every << 16;  fresh | missing_after << 1
 #pragma unroll
     for (int it = 0; it < G; ++it) {
@@ -317,10 +331,16 @@ __global__ void __launch_bounds__(64) env_step_kernel(const __grid_constant__ St
       const uint32_t m = (bit_j >> 5) == sub ? (1u << (bit_j & 31)) : 0u;
       uint32_t fe = __popc(v & b) | (__popc(b) << 16);  // counts use the map BEFORE marking (general_env.py:347)
       uint32_t mf = ((b & m & ~v) ? 1u : 0u) | (__popc(b & ~(v | m)) << 1);
-      if (G == 32 && a.words > 32 && base + j < a.n) {  // grids of more than 1024 patches: the remaining words
+      if (kWide) {
+        const uint32_t v2 = tv[kWide ? it : 0], b2 = tb[kWide ? it : 0];
+        const uint32_t m2 = (bit_j >> 5) == sub + 32 ? (1u << (bit_j & 31)) : 0u;
+        fe += __popc(v2 & b2) | (__popc(b2) << 16);
+        mf += ((b2 & m2 & ~v2) ? 1u : 0u) | (__popc(b2 & ~(v2 | m2)) << 1);
+      }
+      if (kWide && a.words > 64 && base + j < a.n) {  // grids of more than 2048 patches: the remaining words
         const long long row = (long long)(base + j) * a.words;
 #pragma unroll 1
-        for (int w = sub + 32; w < a.words; w += 32) {
+        for (int w = sub + 64; w < a.words; w += 32) {
           const uint32_t v2 = a.visited[row + w], b2 = a.bbox[row + w];
           const uint32_t m2 = (bit_j >> 5) == w ? (1u << (bit_j & 31)) : 0u;
           fe += __popc(v2 & b2) | (__popc(b2) << 16);

@@ -66,6 +66,7 @@ struct GatherArgs {
   // depend on the step kernel it was launched behind
   const int64_t* actions;
   int grid_rows, grid_cols;
+  int stream_stores;            // 1 = the converting kernel writes with st.global.cs (uint8 sources; JN_STREAM_STORES)
   int wait_prior;               // 1 = griddepcontrol.wait before the first index load (src_index comes from the step kernel)
 };
 
@@ -295,6 +296,7 @@ __device__ __forceinline__ void xform_chunk(const GatherArgs& a, const StageDesc
   // frame clipping (translated + padded sets only): uniform over the chunk
   const int row_lim = kShift ? desc_row_limit(d.flags) : a.rows, col_lim = kShift ? desc_col_limit(d.flags) : P;
   const bool clip = kShift && (row_lim < a.rows || col_lim < P);
+  const bool cs = a.stream_stores != 0;
   float* out_item = reinterpret_cast<float*>(d.dst);
   if (kMode == kNormPlain || kMode == kF32Plain) {
     // rows * P source pixels in, rows * P floats out, contiguous in the output
@@ -315,11 +317,13 @@ __device__ __forceinline__ void xform_chunk(const GatherArgs& a, const StageDesc
       if (kMode == kNormPlain) {
         uint32_t u = staged_u8x4<kShift>(row, g, off);
         if (clip) u = clip_u8x4(u, i, g, a.rows, wpr, magic, row_lim, col_lim);
-        st_f4(dst + 4 * i, byte_to_unit<0>(u), byte_to_unit<1>(u), byte_to_unit<2>(u), byte_to_unit<3>(u));
+        if (cs) st_f4_cs(dst + 4 * i, byte_to_unit<0>(u), byte_to_unit<1>(u), byte_to_unit<2>(u), byte_to_unit<3>(u));
+        else st_f4(dst + 4 * i, byte_to_unit<0>(u), byte_to_unit<1>(u), byte_to_unit<2>(u), byte_to_unit<3>(u));
       } else {
         float4 v = staged_f32x4<kShift>(row, g, off);
         if (clip) v = clip_f32x4(v, i, g, a.rows, wpr, magic, row_lim, col_lim);
-        st_f4(dst + 4 * i, v.x, v.y, v.z, v.w);
+        if (cs) st_f4_cs(dst + 4 * i, v.x, v.y, v.z, v.w);
+        else st_f4(dst + 4 * i, v.x, v.y, v.z, v.w);
       }
     }
   } else {
@@ -352,8 +356,8 @@ __device__ __forceinline__ void xform_chunk(const GatherArgs& a, const StageDesc
         e0 = byte_to_unit<0>(u); o0 = byte_to_unit<1>(u); e1 = byte_to_unit<2>(u); o1 = byte_to_unit<3>(u);
       }
       float* even = base + ((r & 1) * dy_planes + (r >> 1) * half + 2 * g);
-      st_f2(even, e0, e1);
-      st_f2(even + dx_planes, o0, o1);
+      if (cs) { st_f2_cs(even, e0, e1); st_f2_cs(even + dx_planes, o0, o1); }
+      else { st_f2(even, e0, e1); st_f2(even + dx_planes, o0, o1); }
     }
   }
 }

@@ -231,10 +231,12 @@ def test_cfg4_geometry_8192_patch256_seq32():
     env.check_status()
 
 
-@pytest.mark.parametrize("gh,gw", [(40, 36), (33, 33), (6, 11), (1, 70)])
+@pytest.mark.parametrize("gh,gw", [(40, 36), (33, 33), (6, 11), (1, 70), (64, 32), (50, 50), (46, 45)])
 def test_grids_of_more_than_32_bitmap_words(gh, gw):
-    """Grids beyond 1024 patches (40x36 = 45 bitmap words: the step kernel's lanes loop over the words), just
-    past it (33x33 = 35 words), three words, and a single row of 70 patches -- every output against the oracle."""
+    """Grids beyond 1024 patches (40x36 = 45 bitmap words: the step kernel keeps a second block of 32 words in
+    registers), just past it (33x33 = 35 words), three words, a single row of 70 patches, exactly two blocks
+    (64x32 = 64 words), and past them (50x50 = 79 words, 46x45 = 65: the lanes loop over the rest) -- every output
+    against the oracle."""
     b, P, T = 37, 8, 12  # 37 episodes: two warps of the lane-per-episode kernel, the second one partial
     rng = np.random.default_rng(gh * 100 + gw)
     u8 = synth_u8(b, 3, gh * P, gw * P, salt=gh)

@@ -52,6 +52,19 @@ if [ "$arg" = "ncu" ]; then
   $CMD > $D/plain_sup2.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:"gather_xform|traj_expand" -s 6 -c 3 -o $D/prof_supervised $CMD > $D/ncu_sup.log 2>&1
   note "ncu cfg2 rc=$?"
+  # single-launch captures of the microbenches: Focus gather, float32 pass-through, step kernel on a 45-word grid
+  CMD="python tools/microbench_gather.py --patches 448 --batches 2048 --modes u8 --layouts focus --engines auto"
+  $CMD > $D/plain_focus.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:gather_xform -s 6 -c 1 -o $D/prof_focus $CMD > $D/ncu_focus.log 2>&1
+  note "ncu micro focus rc=$?"
+  CMD="python tools/microbench_gather.py --patches 448 --batches 2048 --modes f32 --layouts plain --engines auto"
+  $CMD > $D/plain_f32.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:gather_xform -s 6 -c 1 -o $D/prof_f32plain $CMD > $D/ncu_f32.log 2>&1
+  note "ncu micro f32 rc=$?"
+  CMD="python tools/microbench_step.py --grids 40x36,32x32,8x8 --batches 8192"
+  $CMD > $D/plain_step.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:env_step -s 20 -c 1 -o $D/prof_step4036 $CMD > $D/ncu_step.log 2>&1
+  note "ncu micro step rc=$?"
 fi
 done
 cat $D/summary.txt
