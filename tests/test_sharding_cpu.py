@@ -44,7 +44,7 @@ def _worker(rank, world, port, results):
 
 def test_world_size_two_gloo():
     world, port = 2, _free_port()
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()  # (fork from a multi-threaded pytest process can deadlock)
     results = mgr.dict()
     mp.spawn(_worker, args=(world, port, results), nprocs=world, join=True)
     assert len(results) == 2
